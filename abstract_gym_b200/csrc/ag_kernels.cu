@@ -1,0 +1,515 @@
+// ag_kernels.cu -- kernels K1..K5 of the scene_0 hot path and their extern "C" launchers.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (abstract_gym_b200/build.py).
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+
+#include "ag_device.cuh"
+#include "ag_fast.cuh"
+
+using namespace agd;
+
+namespace {
+
+constexpr int AG_BLOCK = 256;
+std::atomic<long long> g_launches{0};
+
+struct RolloutDev {
+    int64_t n, env_id0, row_stride;
+    int32_t K, R;
+    uint64_t seed;
+    const float *actions;
+    const double *reset_u;
+    double *j1, *j2;
+    float *reward;
+    uint8_t *flags;
+    uint32_t *step_ctr, *reset_ctr, *ep_len;
+    float *rec_j1, *rec_j2, *rec_reward;
+    uint8_t *rec_flags;
+    unsigned long long *stats;
+};
+
+__device__ __forceinline__ GridView thread_grid_view(const GridDev &G, int64_t gid) {
+    GridView V;
+    V.bits = G.bits + grid_of_env(G, gid) * G.stride_words;
+    V.min_x = G.min_x; V.min_y = G.min_y;
+    return V;
+}
+
+// ------------------------------------------------------------------------------------------- K5
+// environment/occupancy_grid.py:35-37,85-90: matrix -> set of occupied cells, here one bit per cell.
+__global__ void k_grid_pack(const uint8_t *__restrict__ occ, int S, int wpr, int n_grids, uint32_t *__restrict__ bits,
+                            int64_t stride_words) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per_grid = (int64_t)S * wpr;
+    if (i >= per_grid * n_grids) return;
+    const int64_t g = i / per_grid;
+    const int r = (int)((i % per_grid) / wpr), w = (int)(i % wpr);
+    const uint8_t *row = occ + (g * S + r) * (int64_t)S;
+    uint32_t word = 0;
+    const int c_end = min(S, (w + 1) * 32);
+    for (int c = w * 32; c < c_end; ++c) word |= (row[c] != 0 ? 1u : 0u) << (c & 31);
+    bits[g * stride_words + (int64_t)r * wpr + w] = word;
+}
+
+// ------------------------------------------------------------------------- predicate / FK arrays
+__global__ void k_segment_square(const double *__restrict__ seg, const double *__restrict__ sq, double eps,
+                                 uint8_t *__restrict__ hit, double *__restrict__ abc, double *__restrict__ corner_values,
+                                 unsigned long long *axis_aligned, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 s = reinterpret_cast<const double4 *>(seg)[i];
+    const double4 q = reinterpret_cast<const double4 *>(sq)[i];
+    int axis = 0;
+    const LineD L = make_line(s.x, s.y, s.z, s.w);       // utils/collision_checker.py:21
+    hit[i] = segment_square_exact(L, q.x, q.y, q.z, q.w, eps, axis) ? 1 : 0;
+    if (abc) { abc[3 * i] = L.a; abc[3 * i + 1] = L.b; abc[3 * i + 2] = L.c; }
+    if (corner_values) {                                 // utils/collision_checker.py:27-30
+        const double ax0 = __dmul_rn(L.a, q.x), ax1 = __dmul_rn(L.a, q.z);
+        const double by0 = __dmul_rn(L.b, q.y), by1 = __dmul_rn(L.b, q.w);
+        corner_values[4 * i] = __dadd_rn(__dadd_rn(ax0, by0), L.c);
+        corner_values[4 * i + 1] = __dadd_rn(__dadd_rn(ax0, by1), L.c);
+        corner_values[4 * i + 2] = __dadd_rn(__dadd_rn(ax1, by0), L.c);
+        corner_values[4 * i + 3] = __dadd_rn(__dadd_rn(ax1, by1), L.c);
+    }
+    if (axis && axis_aligned) atomicAdd(axis_aligned, (unsigned long long)axis);
+}
+
+__global__ void k_forward_kinematics(ag_params P, const double *__restrict__ j1, const double *__restrict__ j2,
+                                     double *__restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Arm A = forward_kinematics(j1[i], j2[i], P.link_1, P.link_2);
+    reinterpret_cast<double4 *>(out)[i] = make_double4(A.ex, A.ey, A.gx, A.gy);
+}
+
+// engine dispatch shared by K1..K3: FAST decides with the float32 filter and re-evaluates the
+// undecided lanes with the EXACT engine (ag_fast.cuh), so all engines return the same flag.
+// NEED_ARM: the caller wants the float64 arm A (K1's ee/dist outputs and reach test).
+template <int ENGINE, bool WANT_FIRST, bool NEED_ARM>
+__device__ __forceinline__ bool pose_collides(const ag_params &P, const GridDev &G, const GridView &V, double j1,
+                                              double j2, Arm &A, int &fh, int &axis) {
+    if constexpr (ENGINE == AG_ENGINE_FAST && !WANT_FIRST) {
+        if constexpr (NEED_ARM) {
+            A = forward_kinematics(j1, j2, P.link_1, P.link_2);
+            return fast_arm_collides(P, G, V, A, axis);
+        } else {
+            return fast_pose_collides(P, G, V, j1, j2, axis);
+        }
+    } else {
+        A = forward_kinematics(j1, j2, P.link_1, P.link_2);
+        return arm_collides<ENGINE == AG_ENGINE_BRUTE ? AG_ENGINE_BRUTE : AG_ENGINE_EXACT, WANT_FIRST>(
+            G, V, A, P.section_eps, fh, axis);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- K2
+template <int ENGINE, bool WANT_FIRST>
+__global__ void __launch_bounds__(AG_BLOCK) k_collision(const ag_params P, const GridDev G,
+                                                        const double *__restrict__ j1, const double *__restrict__ j2,
+                                                        uint8_t *__restrict__ hit, int32_t *__restrict__ first_hit,
+                                                        int64_t n, int64_t env_id0) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
+    GridView V;
+    if (G.stage) V = stage_grid(G, env_id0 + e0, smem);
+    else V = thread_grid_view(G, env_id0 + min(e, n - 1));
+    if (e >= n) return;
+    Arm A;
+    int fh = INT_MAX, axis = 0;
+    const bool h = pose_collides<ENGINE, WANT_FIRST, false>(P, G, V, j1[e], j2[e], A, fh, axis);
+    hit[e] = h ? 1 : 0;
+    if (WANT_FIRST) first_hit[e] = h ? fh : -1;
+}
+
+// ------------------------------------------------------------------------------------------- K1
+// scenario/scene_0.py:88-103
+template <int ENGINE, bool ACT_F32, bool WANT_FIRST>
+__global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const GridDev G, double *__restrict__ j1,
+                                                   double *__restrict__ j2, const void *__restrict__ actions,
+                                                   float *__restrict__ reward, uint8_t *__restrict__ flags,
+                                                   double *__restrict__ ee, double *__restrict__ dist,
+                                                   int32_t *__restrict__ first_hit, unsigned long long *stats,
+                                                   int64_t n, int64_t env_id0) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned long long s_acc[AG_ST_COUNT];
+    if (threadIdx.x < AG_ST_COUNT) s_acc[threadIdx.x] = 0;
+    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
+    GridView V;
+    if (G.stage) V = stage_grid(G, env_id0 + e0, smem);
+    else V = thread_grid_view(G, env_id0 + min(e, n - 1));
+    __syncthreads();
+    long long st[AG_ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (e < n) {
+        double d1, d2;
+        if (ACT_F32) {
+            const float2 a = reinterpret_cast<const float2 *>(actions)[e];
+            d1 = (double)a.x; d2 = (double)a.y;
+        } else {
+            const double2 a = reinterpret_cast<const double2 *>(actions)[e];
+            d1 = a.x; d2 = a.y;
+        }
+        const double q1 = __dadd_rn(j1[e], d1), q2 = __dadd_rn(j2[e], d2);   // two_joint_robot.py:71-72
+        float rw = reward[e];
+        uint8_t fl = flags[e];
+        Arm A;
+        int fh = INT_MAX, axis = 0;
+        const bool h = pose_collides<ENGINE, WANT_FIRST, true>(P, G, V, q1, q2, A, fh, axis);
+        if (h) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }       // scene_0.py:95-97
+        if (target_reached(P, q1, q2, A)) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }   // :98-100
+        j1[e] = q1; j2[e] = q2; reward[e] = rw; flags[e] = fl;
+        if (ee) reinterpret_cast<double2 *>(ee)[e] = make_double2(A.gx, A.gy);
+        if (dist)
+            reinterpret_cast<double2 *>(dist)[e] =
+                make_double2(fabs(__dsub_rn(P.target_x, A.gx)), fabs(__dsub_rn(P.target_y, A.gy)));
+        if (WANT_FIRST) first_hit[e] = h ? fh : -1;
+        st[AG_ST_ENV_STEPS] = 1;
+        st[AG_ST_AXIS_ALIGNED] = axis;
+    }
+    if (stats) block_accumulate_stats(st, stats, s_acc);
+}
+
+// shared by K3 and K4: scenario/scene_0.py:174-181 with a bound.  `colliding` is the
+// collision_check() of the current pose.
+template <int ENGINE, bool HAS_RESET_U>
+__device__ __forceinline__ void resample_pose(const ag_params &P, const GridDev &G, const GridView &V, bool colliding,
+                                              double &j1, double &j2, uint32_t &rc, const double *reset_u_env,
+                                              int32_t R, uint64_t seed, uint64_t gid, long long (&st)[AG_ST_COUNT]) {
+    int tries = 0;
+    while (colliding) {
+        if (tries >= P.max_reset_tries || (HAS_RESET_U && rc >= (uint32_t)R)) { ++st[AG_ST_STUCK_RESETS]; break; }
+        double u0, u1;
+        if (HAS_RESET_U) {
+            const double2 u = reinterpret_cast<const double2 *>(reset_u_env)[rc];
+            u0 = u.x; u1 = u.y;
+        } else {
+            philox_uniform2(seed, gid, rc, 1u, u0, u1);
+        }
+        ++rc; ++tries;
+        j1 = __dmul_rn(__dmul_rn(u0, 3.141592653589793), 2.0);    // scene_0.py:180  rand()*pi*2.0
+        j2 = __dmul_rn(__dmul_rn(u1, 3.141592653589793), 2.0);    // :181
+        Arm B;
+        int fh = 0, axis = 0;
+        colliding = pose_collides<ENGINE, false, false>(P, G, V, j1, j2, B, fh, axis);
+        st[AG_ST_AXIS_ALIGNED] += axis;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- K3
+// scenario/scene_0.py:105-113 (clear_flags) / :174-181
+template <int ENGINE, bool HAS_RESET_U>
+__global__ void __launch_bounds__(AG_BLOCK) k_reset(const ag_params P, const GridDev G, double *__restrict__ j1,
+                                                    double *__restrict__ j2, float *__restrict__ reward,
+                                                    uint8_t *__restrict__ flags, uint32_t *__restrict__ reset_ctr,
+                                                    const uint8_t *__restrict__ mask, const double *__restrict__ reset_u,
+                                                    int32_t R, uint64_t seed, int clear_flags, unsigned long long *stats,
+                                                    int64_t n, int64_t env_id0) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned long long s_acc[AG_ST_COUNT];
+    if (threadIdx.x < AG_ST_COUNT) s_acc[threadIdx.x] = 0;
+    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
+    GridView V;
+    if (G.stage) V = stage_grid(G, env_id0 + e0, smem);
+    else V = thread_grid_view(G, env_id0 + min(e, n - 1));
+    __syncthreads();
+    long long st[AG_ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (e < n && (mask == nullptr || mask[e] != 0)) {
+        double q1 = j1[e], q2 = j2[e];
+        uint32_t rc = reset_ctr[e];
+        Arm A;
+        int fh = 0, axis = 0;
+        const bool h = pose_collides<ENGINE, false, false>(P, G, V, q1, q2, A, fh, axis);
+        st[AG_ST_AXIS_ALIGNED] += axis;
+        resample_pose<ENGINE, HAS_RESET_U>(P, G, V, h, q1, q2, rc, HAS_RESET_U ? reset_u + (int64_t)e * R * 2 : nullptr,
+                                           R, seed, (uint64_t)(env_id0 + e), st);
+        j1[e] = q1; j2[e] = q2; reset_ctr[e] = rc;
+        if (clear_flags) { reward[e] = 0.0f; flags[e] = 0; }       // scene_0.py:111-113
+    }
+    if (stats) block_accumulate_stats(st, stats, s_acc);
+}
+
+// ------------------------------------------------------------------------------------------- K4
+// experiment/experiment_0.py:20-34 fused over K steps; env state lives in registers for the
+// whole launch, the only per-step HBM traffic is the action read and the record write.
+template <int ENGINE, bool HAS_ACT, bool HAS_RESET_U, bool RECORD>
+__global__ void __launch_bounds__(AG_BLOCK) k_rollout(const ag_params P, const GridDev G, const RolloutDev A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned long long s_acc[AG_ST_COUNT];
+    if (threadIdx.x < AG_ST_COUNT) s_acc[threadIdx.x] = 0;
+    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
+    GridView V;
+    if (G.stage) V = stage_grid(G, A.env_id0 + e0, smem);
+    else V = thread_grid_view(G, A.env_id0 + min(e, A.n - 1));
+    __syncthreads();
+    long long st[AG_ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (e < A.n) {
+        const uint64_t gid = (uint64_t)(A.env_id0 + e);
+        double q1 = A.j1[e], q2 = A.j2[e];
+        float rw = A.reward[e];
+        uint32_t fl = A.flags[e];
+        uint32_t sc = A.step_ctr[e], rc = A.reset_ctr[e], el = A.ep_len[e];
+        const float2 *act = HAS_ACT ? reinterpret_cast<const float2 *>(A.actions) + e : nullptr;
+        const double *ru = HAS_RESET_U ? A.reset_u + (int64_t)e * A.R * 2 : nullptr;
+        for (int t = 0; t < A.K; ++t) {
+            double d1, d2;
+            if (HAS_ACT) {
+                const float2 a = __ldcs(act + (int64_t)t * A.row_stride);   // streamed once
+                d1 = (double)a.x; d2 = (double)a.y;
+            } else {
+                double u0, u1;
+                philox_uniform2(A.seed, gid, sc, 0u, u0, u1);
+                d1 = __dmul_rn(__dsub_rn(u0, 0.5), P.action_scale);          // scene_0.py:84
+                d2 = __dmul_rn(__dsub_rn(u1, 0.5), P.action_scale);          // :85
+            }
+            ++sc;
+            q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);                  // two_joint_robot.py:71-72
+            bool h, reached;
+            int axis = 0;
+            step_decide<ENGINE>(P, G, V, q1, q2, h, reached, axis);
+            st[AG_ST_AXIS_ALIGNED] += axis;
+            if (h) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }            // scene_0.py:95-97
+            if (reached) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }               // :98-100
+            if (RECORD) {                                                    // experiment_0.py:23-25
+                const int64_t o = (int64_t)t * A.row_stride + e;
+                __stcs(A.rec_j1 + o, (float)q1);
+                __stcs(A.rec_j2 + o, (float)q2);
+                __stcs(A.rec_reward + o, rw);
+                A.rec_flags[o] = (uint8_t)fl;
+            }
+            ++el;
+            if (fl) {                                                        // experiment_0.py:30-34
+                ++st[AG_ST_EPISODES];
+                st[AG_ST_COLLISIONS] += (fl & AG_FLAG_COLLISION) ? 1 : 0;
+                st[AG_ST_SUCCESSES] += (fl & AG_FLAG_DONE) ? 1 : 0;
+                st[AG_ST_EP_LEN_SUM] += el;
+                st[AG_ST_RETURN_MILLI] += llrintf(rw * 1e-3f);
+                el = 0;
+                // Scene.reset(): the pose is unchanged since the step, so collision_check() == h
+                resample_pose<ENGINE, HAS_RESET_U>(P, G, V, h, q1, q2, rc, ru, A.R, A.seed, gid, st);
+                rw = 0.0f; fl = 0;                                           // scene_0.py:111-113
+            }
+        }
+        st[AG_ST_ENV_STEPS] = A.K;
+        A.j1[e] = q1; A.j2[e] = q2; A.reward[e] = rw; A.flags[e] = (uint8_t)fl;
+        A.step_ctr[e] = sc; A.reset_ctr[e] = rc; A.ep_len[e] = el;
+    }
+    block_accumulate_stats(st, A.stats, s_acc);
+}
+
+// ------------------------------------------------------------------------------------- host side
+int stage_max_bytes() {
+    static int v = [] {
+        const char *s = std::getenv("AG_STAGE_MAX_BYTES");
+        return s ? std::atoi(s) : 32768;
+    }();
+    return v;
+}
+
+ag_status make_grid_dev(const ag_grid *g, int64_t env_id0, GridDev *out, size_t *smem_bytes) {
+    if (!g || !g->bits || !g->min_x || !g->min_y) return AG_ERR_NULL;
+    if (g->S < 2 || g->words_per_row != (g->S + 31) / 32 || g->n_grids < 1 || g->envs_per_grid < 1 ||
+        g->grid_stride_words < (int64_t)g->S * g->words_per_row)
+        return AG_ERR_SHAPE;
+    GridDev d;
+    d.bits = g->bits; d.min_x = g->min_x; d.min_y = g->min_y;
+    d.side = g->side; d.half = g->env_size / 2.0; d.inv_side = 1.0 / g->side;
+    d.margin = 1e-9 * g->env_size;
+    d.S = g->S; d.wpr = g->words_per_row; d.n_grids = g->n_grids;
+    d.stride_words = g->grid_stride_words; d.envs_per_grid = g->envs_per_grid;
+    const int spad = (g->S + 1) & ~1;
+    const size_t bytes = 16 + (size_t)g->grid_stride_words * 4 + (size_t)spad * 16;
+    const bool uniform = g->n_grids == 1 || (g->envs_per_grid % AG_BLOCK == 0 && env_id0 % AG_BLOCK == 0);
+    const bool aligned = ((uintptr_t)g->bits % 16 == 0) && (g->grid_stride_words % 4 == 0);
+    d.stage = (uniform && aligned && bytes <= (size_t)stage_max_bytes()) ? 1 : 0;
+    *smem_bytes = d.stage ? bytes : 0;
+    *out = d;
+    return AG_OK;
+}
+
+template <typename Kern>
+ag_status set_smem(Kern k, size_t smem) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (ag_status)e;
+    }
+    return AG_OK;
+}
+
+inline ag_status launched() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (ag_status)cudaGetLastError();
+}
+
+inline unsigned blocks_for(int64_t n) { return (unsigned)((n + AG_BLOCK - 1) / AG_BLOCK); }
+
+#define AG_DISPATCH_ENGINE(engine, ...)                                   \
+    switch (engine) {                                                     \
+        case AG_ENGINE_EXACT: { constexpr int E = AG_ENGINE_EXACT; __VA_ARGS__; break; } \
+        case AG_ENGINE_FAST:  { constexpr int E = AG_ENGINE_FAST;  __VA_ARGS__; break; } \
+        case AG_ENGINE_BRUTE: { constexpr int E = AG_ENGINE_BRUTE; __VA_ARGS__; break; } \
+        default: return AG_ERR_MODE;                                      \
+    }
+
+template <int E, bool HA, bool HR, bool REC>
+ag_status launch_rollout_t(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s) {
+    auto k = k_rollout<E, HA, HR, REC>;
+    ag_status st = set_smem(k, smem);
+    if (st) return st;
+    k<<<blocks_for(A.n), AG_BLOCK, smem, s>>>(P, G, A);
+    return launched();
+}
+
+template <int E>
+ag_status launch_rollout_e(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s) {
+    const bool ha = A.actions != nullptr, hr = A.reset_u != nullptr, rec = A.rec_j1 != nullptr;
+#define AG_RO(HA, HR, REC) return launch_rollout_t<E, HA, HR, REC>(P, G, A, smem, s)
+    if (ha) { if (hr) { if (rec) AG_RO(true, true, true); else AG_RO(true, true, false); }
+              else    { if (rec) AG_RO(true, false, true); else AG_RO(true, false, false); } }
+    else    { if (hr) { if (rec) AG_RO(false, true, true); else AG_RO(false, true, false); }
+              else    { if (rec) AG_RO(false, false, true); else AG_RO(false, false, false); } }
+#undef AG_RO
+}
+
+}  // namespace
+
+// internal (used by ag_host.cu): rollout with explicit grid descriptor validation done
+ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, int64_t row_stride,
+                          void *stream) {
+    if (!p || !g || !a) return AG_ERR_NULL;
+    if (a->n < 0 || a->K < 1) return AG_ERR_SHAPE;
+    if (a->n == 0) return AG_OK;
+    if (!a->j1 || !a->j2 || !a->reward || !a->flags || !a->step_ctr || !a->reset_ctr || !a->ep_len || !a->stats)
+        return AG_ERR_NULL;
+    const int nrec = (a->rec_j1 != nullptr) + (a->rec_j2 != nullptr) + (a->rec_reward != nullptr) + (a->rec_flags != nullptr);
+    if (nrec != 0 && nrec != 4) return AG_ERR_NULL;
+    if (a->reset_u && a->R < 1) return AG_ERR_SHAPE;
+    if (((uintptr_t)a->actions % 8) || ((uintptr_t)a->reset_u % 16)) return AG_ERR_ALIGN;
+    if (row_stride < a->n) return AG_ERR_SHAPE;
+    GridDev G;
+    size_t smem;
+    ag_status st = make_grid_dev(g, a->env_id0, &G, &smem);
+    if (st) return st;
+    RolloutDev A;
+    A.n = a->n; A.env_id0 = a->env_id0; A.row_stride = row_stride; A.K = a->K; A.R = a->R; A.seed = a->seed;
+    A.actions = a->actions; A.reset_u = a->reset_u;
+    A.j1 = a->j1; A.j2 = a->j2; A.reward = a->reward; A.flags = a->flags;
+    A.step_ctr = a->step_ctr; A.reset_ctr = a->reset_ctr; A.ep_len = a->ep_len;
+    A.rec_j1 = a->rec_j1; A.rec_j2 = a->rec_j2; A.rec_reward = a->rec_reward; A.rec_flags = a->rec_flags;
+    A.stats = reinterpret_cast<unsigned long long *>(a->stats);
+    cudaStream_t s = (cudaStream_t)stream;
+    AG_DISPATCH_ENGINE(a->engine, return launch_rollout_e<E>(*p, G, A, smem, s));
+    return AG_OK;
+}
+
+extern "C" {
+
+int64_t ag_launch_count(void) { return g_launches.load(); }
+
+ag_status ag_grid_pack(const uint8_t *occ, int32_t S, int32_t n_grids, uint32_t *bits, int64_t grid_stride_words,
+                       void *stream) {
+    if (!occ || !bits) return AG_ERR_NULL;
+    const int wpr = (S + 31) / 32;
+    if (S < 2 || n_grids < 1 || grid_stride_words < (int64_t)S * wpr) return AG_ERR_SHAPE;
+    const int64_t total = (int64_t)S * wpr * n_grids;
+    k_grid_pack<<<blocks_for(total), AG_BLOCK, 0, (cudaStream_t)stream>>>(occ, S, wpr, n_grids, bits, grid_stride_words);
+    return launched();
+}
+
+ag_status ag_segment_square(const double *seg, const double *sq, double section_eps, uint8_t *hit, double *abc,
+                            double *corner_values, int64_t *axis_aligned, int64_t n, void *stream) {
+    if (n < 0) return AG_ERR_SHAPE;
+    if (n == 0) return AG_OK;
+    if (!seg || !sq || !hit) return AG_ERR_NULL;
+    if (((uintptr_t)seg % 32) || ((uintptr_t)sq % 32)) return AG_ERR_ALIGN;
+    k_segment_square<<<blocks_for(n), AG_BLOCK, 0, (cudaStream_t)stream>>>(
+        seg, sq, section_eps, hit, abc, corner_values, reinterpret_cast<unsigned long long *>(axis_aligned), n);
+    return launched();
+}
+
+ag_status ag_forward_kinematics(const ag_params *p, const double *j1, const double *j2, double *out, int64_t n,
+                                void *stream) {
+    if (n < 0) return AG_ERR_SHAPE;
+    if (n == 0) return AG_OK;
+    if (!p || !j1 || !j2 || !out) return AG_ERR_NULL;
+    if ((uintptr_t)out % 32) return AG_ERR_ALIGN;
+    k_forward_kinematics<<<blocks_for(n), AG_BLOCK, 0, (cudaStream_t)stream>>>(*p, j1, j2, out, n);
+    return launched();
+}
+
+ag_status ag_collision_check(const ag_params *p, const ag_grid *g, const double *j1, const double *j2, uint8_t *hit,
+                             int32_t *first_hit, int64_t n, int64_t env_id0, int32_t engine, void *stream) {
+    if (n < 0) return AG_ERR_SHAPE;
+    if (!p || !g) return AG_ERR_NULL;
+    GridDev G;
+    size_t smem;
+    ag_status st = make_grid_dev(g, env_id0, &G, &smem);
+    if (st) return st;
+    if (n == 0) return AG_OK;
+    if (!j1 || !j2 || !hit) return AG_ERR_NULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    AG_DISPATCH_ENGINE(engine, {
+        if (first_hit) {
+            auto k = k_collision<E, true>;
+            if ((st = set_smem(k, smem))) return st;
+            k<<<blocks_for(n), AG_BLOCK, smem, s>>>(*p, G, j1, j2, hit, first_hit, n, env_id0);
+        } else {
+            auto k = k_collision<E, false>;
+            if ((st = set_smem(k, smem))) return st;
+            k<<<blocks_for(n), AG_BLOCK, smem, s>>>(*p, G, j1, j2, hit, first_hit, n, env_id0);
+        }
+    });
+    return launched();
+}
+
+ag_status ag_step(const ag_params *p, const ag_grid *g, double *j1, double *j2, const void *actions,
+                  int32_t actions_f32, float *reward, uint8_t *flags, double *ee, double *dist, int32_t *first_hit,
+                  int64_t *stats, int64_t n, int64_t env_id0, int32_t engine, void *stream) {
+    if (n < 0) return AG_ERR_SHAPE;
+    if (!p || !g) return AG_ERR_NULL;
+    GridDev G;
+    size_t smem;
+    ag_status st = make_grid_dev(g, env_id0, &G, &smem);
+    if (st) return st;
+    if (n == 0) return AG_OK;
+    if (!j1 || !j2 || !actions || !reward || !flags) return AG_ERR_NULL;
+    if (((uintptr_t)actions % (actions_f32 ? 8 : 16)) || ((uintptr_t)ee % 16) || ((uintptr_t)dist % 16)) return AG_ERR_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *ust = reinterpret_cast<unsigned long long *>(stats);
+#define AG_STEP(F32, WF) { auto k = k_step<E, F32, WF>; if ((st = set_smem(k, smem))) return st; \
+        k<<<blocks_for(n), AG_BLOCK, smem, s>>>(*p, G, j1, j2, actions, reward, flags, ee, dist, first_hit, ust, n, env_id0); }
+    AG_DISPATCH_ENGINE(engine, {
+        if (actions_f32) { if (first_hit) AG_STEP(true, true) else AG_STEP(true, false) }
+        else             { if (first_hit) AG_STEP(false, true) else AG_STEP(false, false) }
+    });
+#undef AG_STEP
+    return launched();
+}
+
+ag_status ag_reset(const ag_params *p, const ag_grid *g, double *j1, double *j2, float *reward, uint8_t *flags,
+                   uint32_t *reset_ctr, const uint8_t *mask, const double *reset_u, int32_t R, uint64_t seed,
+                   int32_t clear_flags, int64_t *stats, int64_t n, int64_t env_id0, int32_t engine, void *stream) {
+    if (n < 0) return AG_ERR_SHAPE;
+    if (!p || !g) return AG_ERR_NULL;
+    GridDev G;
+    size_t smem;
+    ag_status st = make_grid_dev(g, env_id0, &G, &smem);
+    if (st) return st;
+    if (n == 0) return AG_OK;
+    if (!j1 || !j2 || !reset_ctr || (clear_flags && (!reward || !flags))) return AG_ERR_NULL;
+    if (reset_u && R < 1) return AG_ERR_SHAPE;
+    if ((uintptr_t)reset_u % 16) return AG_ERR_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *ust = reinterpret_cast<unsigned long long *>(stats);
+#define AG_RESET(HR) { auto k = k_reset<E, HR>; if ((st = set_smem(k, smem))) return st; \
+        k<<<blocks_for(n), AG_BLOCK, smem, s>>>(*p, G, j1, j2, reward, flags, reset_ctr, mask, reset_u, R, seed, clear_flags, ust, n, env_id0); }
+    AG_DISPATCH_ENGINE(engine, { if (reset_u) AG_RESET(true) else AG_RESET(false) });
+#undef AG_RESET
+    return launched();
+}
+
+ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream) {
+    if (!a) return AG_ERR_NULL;
+    return ag_rollout_impl(p, g, a, a->n, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+"""Occupancy grids: the reference's `OccupancyGrid` (environment/occupancy_grid.py:7-93) plus the
+device-side form the kernels read (bit-packed rows + float64 corner tables) and a batched
+many-grids variant.
+
+Frame convention, reproduced from environment/occupancy_grid.py:28,59-67: S cells per side, each
+of side E/(S-1); cell (row r, col c) has bottom-left corner ((c*E)/(S-1) - E/2, -((r*E)/(S-1) - E/2));
+row 0 is the TOP row; the grid is not centred.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._device import ptr, require_cuda, stream_ptr
+from ..utils.geometry import Point, Square
+
+
+class DeviceGrid:
+    """What the kernels read: bits[n_grids][stride_words] uint32, min_x[S], min_y[S] float64."""
+
+    def __init__(self, bits, S, environment_size, n_grids=1, envs_per_grid=1 << 62, device=None):
+        lib = _lib.load()
+        self.device = bits.device
+        self.S = int(S)
+        self.environment_size = float(environment_size)
+        self.words_per_row = int(lib.ag_grid_words_per_row(self.S))
+        self.stride_words = int(lib.ag_grid_stride_words(self.S))
+        self.n_grids = int(n_grids)
+        self.envs_per_grid = int(envs_per_grid)
+        assert bits.dtype == torch.int32 and bits.numel() == self.n_grids * self.stride_words
+        self.bits = bits
+        spad = (self.S + 1) & ~1
+        mx = np.zeros(spad, dtype=np.float64)
+        my = np.zeros(spad, dtype=np.float64)
+        side = C.c_double()
+        _lib.check(lib.ag_grid_tables_host(self.S, self.environment_size, mx.ctypes.data_as(C.c_void_p),
+                                           my.ctypes.data_as(C.c_void_p), C.byref(side)), "ag_grid_tables_host")
+        self.side = side.value
+        self.min_x_host, self.min_y_host = mx[:self.S].copy(), my[:self.S].copy()
+        self.min_x = torch.from_numpy(mx).to(self.device)
+        self.min_y = torch.from_numpy(my).to(self.device)
+
+    def c_struct(self, envs_per_grid=None) -> _lib.Grid:
+        g = _lib.Grid()
+        g.bits, g.min_x, g.min_y = self.bits.data_ptr(), self.min_x.data_ptr(), self.min_y.data_ptr()
+        g.side, g.env_size = self.side, self.environment_size
+        g.S, g.words_per_row, g.n_grids = self.S, self.words_per_row, self.n_grids
+        g.grid_stride_words = self.stride_words
+        g.envs_per_grid = self.envs_per_grid if envs_per_grid is None else int(envs_per_grid)
+        return g
+
+    @classmethod
+    def from_host_matrix(cls, occ, environment_size=1.6, device=None):
+        dev = require_cuda(device)
+        lib = _lib.load()
+        occ8 = np.ascontiguousarray(np.asarray(occ) != 0, dtype=np.uint8)
+        if occ8.ndim != 2:
+            raise ValueError("occupancy matrix must be 2-D")
+        words = np.zeros(int(lib.ag_grid_stride_words(occ8.shape[0])), dtype=np.uint32)
+        _lib.check(lib.ag_grid_pack_host(occ8.ctypes.data_as(C.c_void_p), occ8.shape[0], occ8.shape[1],
+                                         words.ctypes.data_as(C.c_void_p)), "ag_grid_pack_host")
+        bits = torch.from_numpy(words.view(np.int32)).to(dev)
+        return cls(bits, occ8.shape[0], environment_size)
+
+    @classmethod
+    def from_device_matrices(cls, occ, environment_size=1.6, envs_per_grid=1 << 62):
+        """occ: [G,S,S] CUDA tensor (any integer/bool dtype) -> packed on the device (kernel K5)."""
+        if occ.dim() == 2:
+            occ = occ.unsqueeze(0)
+        if occ.dim() != 3 or occ.shape[1] != occ.shape[2]:
+            raise ValueError("expected [G,S,S] occupancy matrices")
+        dev = require_cuda(occ.device)
+        lib = _lib.load()
+        G, S = occ.shape[0], occ.shape[1]
+        occ8 = (occ != 0).to(torch.uint8).contiguous()
+        stride = int(lib.ag_grid_stride_words(S))
+        bits = torch.zeros(G * stride, dtype=torch.int32, device=dev)
+        _lib.check(lib.ag_grid_pack(ptr(occ8), S, G, ptr(bits), stride, stream_ptr(dev)), "ag_grid_pack")
+        return cls(bits, S, environment_size, n_grids=G, envs_per_grid=envs_per_grid)
+
+    def unpack(self):
+        """[G,S,S] uint8 numpy (inverse of the packing; for tests and tools)"""
+        w = self.bits.cpu().numpy().view(np.uint32).reshape(self.n_grids, self.stride_words)
+        w = w[:, :self.S * self.words_per_row].reshape(self.n_grids, self.S, self.words_per_row)
+        b = ((w[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8)
+        return b.reshape(self.n_grids, self.S, self.words_per_row * 32)[:, :, :self.S]
+
+
+class OccupancyGrid:
+    """Same constructor, attributes and methods as the reference class.
+
+    occ                  : the size x size matrix (non-zero = obstacle)
+    occ_coordinate       : [M,2] bottom-left corners in the robot frame (after transform_frame)
+    obstacle_list        : M `Square`s, in the reference's order
+    obstacle_side_length : environment_size / (size - 1)
+
+    Differences, both counted in DESIGN.md: a grid with no obstacle is accepted (the reference
+    raises ValueError at occupancy_grid.py:64); `manual_cells` lets a caller state the hard-coded
+    example map explicitly."""
+
+    MANUAL_CELLS = ((5, 6), (5, 7), (2, 3))   # (row, col) of occupancy_grid.py:45-47
+
+    def __init__(self, size=9, random_obstacle=True, obstacle_probability=0.1, environment_size=1.6):
+        self.size = size
+        self.environment_size = environment_size
+        self.obstacle_side_length = environment_size / (size - 1)
+        self.obstacle_list = []
+        self._device_grids = {}
+        if random_obstacle:
+            # same draw as the reference (one np.random.random((size,size)) from the global stream)
+            self.occ = np.where(np.random.random((size, size)) < obstacle_probability, 1, 0)
+            rows, cols = np.nonzero(self.occ)
+            self.occ_coordinate = [[c, r] for r, c in zip(rows, cols)]
+        else:
+            self.occ = np.zeros((size, size))
+            self.occ_coordinate = []
+            for r, c in self.MANUAL_CELLS:      # list order of occupancy_grid.py:48-50
+                self.occ[r][c] = 1
+                self.occ_coordinate.append([c, r])
+        self.transform_frame()
+
+    def transform_frame(self):
+        """matrix (col,row) -> robot frame bottom-left corners, then Squares (occupancy_grid.py:54-68)"""
+        self._device_grids = {}
+        self.obstacle_list = []
+        idx = np.array(self.occ_coordinate, dtype=np.int64).reshape(-1, 2)
+        if idx.shape[0] == 0:
+            self.occ_coordinate = np.zeros((0, 2))
+            return
+        xy = idx * self.environment_size / (self.size - 1) - self.environment_size / 2.0
+        xy *= [1, -1]
+        self.occ_coordinate = xy
+        s = self.obstacle_side_length
+        self.obstacle_list = [Square(Point(x, y), Point(x + s, y + s)) for x, y in xy]
+
+    def get_occupancy_grid(self):
+        return self.occ, self.occ_coordinate, self.obstacle_list, self.obstacle_side_length
+
+    def load_from_matrix(self, matrix, environment_size=1.6):
+        """occupancy_grid.py:73-93"""
+        matrix = np.asarray(matrix)
+        if matrix.ndim != 2 or matrix.shape[0] != matrix.shape[1]:
+            print("The matrix is not square.")
+            return
+        self.size = matrix.shape[0]
+        self.occ = np.copy(matrix)
+        self.environment_size = environment_size
+        self.obstacle_side_length = environment_size / (self.size - 1)
+        rows, cols = np.nonzero(self.occ)
+        self.occ_coordinate = [[c, r] for r, c in zip(rows, cols)]
+        self.transform_frame()
+
+    # ---- device form -------------------------------------------------------------------------
+    def device_grid(self, device=None) -> DeviceGrid:
+        dev = require_cuda(device)
+        key = str(dev)
+        if key not in self._device_grids:
+            self._device_grids[key] = DeviceGrid.from_host_matrix(self.occ, self.environment_size, dev)
+        return self._device_grids[key]
+
+
+class BatchedOccupancyGrid:
+    """G distinct S x S grids resident on the device; env with global id e uses grid
+    (e // envs_per_grid) % G (BASELINE config 5: per-env-batch heterogeneous maps)."""
+
+    def __init__(self, occ, envs_per_grid, environment_size=1.6, device=None):
+        dev = require_cuda(device if device is not None else (occ.device if torch.is_tensor(occ) else None))
+        occ_t = torch.as_tensor(occ, device=dev)
+        self._grid = DeviceGrid.from_device_matrices(occ_t, environment_size, envs_per_grid)
+        self.size = self._grid.S
+        self.environment_size = environment_size
+        self.obstacle_side_length = self._grid.side
+        self.envs_per_grid = envs_per_grid
+        self.n_grids = self._grid.n_grids
+
+    @classmethod
+    def random(cls, n_grids, size, obstacle_probability, envs_per_grid, environment_size=1.6, device=None,
+               generator=None):
+        dev = require_cuda(device)
+        occ = torch.rand(n_grids, size, size, device=dev, generator=generator) < obstacle_probability
+        return cls(occ, envs_per_grid, environment_size, dev)
+
+    def device_grid(self, device=None) -> DeviceGrid:
+        return self._grid

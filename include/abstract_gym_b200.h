@@ -1,0 +1,212 @@
+/*
+ * abstract_gym_b200.h -- C ABI of the B200-native batched scene_0 simulator.
+ *
+ * The reference (tualatint/abstract_gym) is pure Python and has no FFI of its own; the boundary it
+ * offers is its class API.  Each entry point below names the reference method it replaces
+ * (file:line relative to the reference root).  The Python host package (abstract_gym_b200/) keeps
+ * the reference's class names/signatures and calls these symbols through ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns ag_status (0 = ok, <0 = argument/shape error, >0 = cudaError_t);
+ *     nothing throws across the boundary; no hidden global state;
+ *   - unless a name ends in _host, every pointer is a DEVICE pointer owned by the caller and all
+ *     work is enqueued on `stream` (a cudaStream_t passed as void*); calls are stream-ordered,
+ *     re-entrant and never synchronise;
+ *   - *_host entry points take HOST pointers, do their own H2D/D2H copies and return after the
+ *     results are in the host buffers;
+ *   - there is no CPU implementation behind any of these symbols: without a CUDA device they
+ *     return cudaErrorNoDevice / cudaErrorInsufficientDriver.
+ */
+#ifndef ABSTRACT_GYM_B200_H
+#define ABSTRACT_GYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define AG_API __attribute__((visibility("default")))
+#else
+#define AG_API
+#endif
+
+typedef int32_t ag_status;
+enum {
+    AG_OK = 0,
+    AG_ERR_NULL = -1,        /* a required pointer is NULL */
+    AG_ERR_SHAPE = -2,       /* n < 0, K < 1, S < 2, bad strides ... */
+    AG_ERR_MODE = -3,        /* unknown mode / unsupported combination */
+    AG_ERR_ALIGN = -4,       /* pointer not aligned as documented */
+    AG_ERR_NOT_SQUARE = -5   /* occupancy matrix is not square (occupancy_grid.py:80-82) */
+};
+
+/* Scene constants: the literals of scenario/scene_0.py:17,30-31,78,96,99,122,
+ * utils/collision_checker.py:81 and robot/two_joint_robot.py:12-13 (ag_default_params fills
+ * them).  Passed by pointer from HOST memory; copied into the launch. */
+typedef struct ag_params {
+    double link_1, link_2;
+    double target_x, target_y;       /* Scene.target_c */
+    double target_j1, target_j2;     /* Scene.target_j */
+    double reach_eps;                /* check_target_reached epsilon */
+    double section_eps;              /* check_sections epsilon */
+    double reward_collision;
+    double reward_reach;
+    double action_scale;             /* sample_action scale_factor */
+    int32_t choose_j_tar;            /* Scene.choose_j_tar */
+    int32_t max_reset_tries;         /* bound on random_valid_pose's loop (unbounded in the reference) */
+} ag_params;
+
+/* Bit-packed occupancy grid(s) + the float64 cell-corner tables (environment/occupancy_grid.py:
+ * 28,59-67).  Bit c%32 of word bits[g*grid_stride_words + r*words_per_row + c/32] is cell
+ * (row r, col c) of grid g; row 0 is the TOP row (y flipped), exactly the reference's `occ` matrix.
+ * min_x[c], min_y[r] hold the reference's rounded corner values; max = min + side.
+ * Env with global id e uses grid (e / envs_per_grid) % n_grids.  Passed from HOST memory; the
+ * pointers inside are DEVICE pointers. */
+typedef struct ag_grid {
+    const uint32_t *bits;
+    const double *min_x;             /* [S] */
+    const double *min_y;             /* [S] */
+    double side;                     /* E / (S-1) */
+    double env_size;                 /* E */
+    int32_t S;
+    int32_t words_per_row;           /* ceil(S/32) */
+    int32_t n_grids;
+    int32_t reserved;
+    int64_t grid_stride_words;       /* >= S*words_per_row, multiple of 4 (16-byte rows for bulk copies) */
+    int64_t envs_per_grid;
+} ag_grid;
+
+/* Collision engine selection. All three return identical flags (tests/test_gpu_parity.py):
+ *   EXACT : float64, reference operation order, conservative cell traversal of the bit grid;
+ *   FAST  : float32 interval filter, float64 EXACT re-evaluation of every undecided lane;
+ *   BRUTE : float64, every occupied cell of the grid (the reference's O(#obstacles) loop,
+ *           scenario/scene_0.py:67) -- the on-device cross-check of the traversal. */
+enum { AG_ENGINE_EXACT = 0, AG_ENGINE_FAST = 1, AG_ENGINE_BRUTE = 2 };
+
+/* sticky flag bits (Scene.collision_status / Scene.done, scenario/scene_0.py:33-40) */
+enum { AG_FLAG_COLLISION = 1, AG_FLAG_DONE = 2 };
+
+/* episode statistics, int64 counters (the reference prints "records:"/"succ:" experiment_0.py:35-36) */
+enum {
+    AG_ST_EPISODES = 0,      /* terminal steps (done or collision) */
+    AG_ST_COLLISIONS,        /* episodes that ended with collision_status set */
+    AG_ST_SUCCESSES,         /* episodes that ended with done set */
+    AG_ST_ENV_STEPS,
+    AG_ST_EP_LEN_SUM,
+    AG_ST_RETURN_MILLI,      /* sum of terminal rewards / 1000 (-1 or +10 each) */
+    AG_ST_STUCK_RESETS,      /* resets that exhausted max_reset_tries / the candidate list */
+    AG_ST_AXIS_ALIGNED,      /* check_sections a==0/b==0 evaluations (AttributeError in the reference) */
+    AG_ST_COUNT
+};
+
+/* ---- host-only helpers (no device needed) ------------------------------------------------- */
+
+AG_API int32_t ag_abi_version(void);
+AG_API const char *ag_status_string(ag_status s);
+AG_API void ag_default_params(ag_params *p);
+AG_API int32_t ag_grid_words_per_row(int32_t S);
+AG_API int64_t ag_grid_stride_words(int32_t S);
+
+/* OccupancyGrid.__init__/load_from_matrix -> packed bits (occupancy_grid.py:25-50,73-93).
+ * occ: rows x cols uint8 host matrix (non-zero = occupied); bits_out: ag_grid_stride_words(S) words. */
+AG_API ag_status ag_grid_pack_host(const uint8_t *occ, int32_t rows, int32_t cols, uint32_t *bits_out);
+/* OccupancyGrid.transform_frame corner arithmetic (occupancy_grid.py:28,59-67), host float64. */
+AG_API ag_status ag_grid_tables_host(int32_t S, double env_size, double *min_x, double *min_y, double *side);
+
+/* ---- device entry points ------------------------------------------------------------------- */
+
+/* K5: pack n_grids S x S uint8 occupancy matrices (device) into bits (device). */
+AG_API ag_status ag_grid_pack(const uint8_t *occ, int32_t S, int32_t n_grids, uint32_t *bits,
+                       int64_t grid_stride_words, void *stream);
+
+/* utils/geometry.py:14-32 Line.compute_line_function() and utils/collision_checker.py:12-46
+ * CollisionChecker(line, square).compute_corner_line_value()/.collision_check() over arrays.
+ * seg: [n][4] (p0x,p0y,p1x,p1y); sq: [n][4] (min_x,min_y,max_x,max_y); hit: [n] uint8.
+ * Optional: abc [n][3] line coefficients; corner_values [n][4] (v1..v4 before np.sign);
+ * axis_aligned int64[1] counter (accumulated). */
+AG_API ag_status ag_segment_square(const double *seg, const double *sq, double section_eps, uint8_t *hit,
+                            double *abc, double *corner_values, int64_t *axis_aligned, int64_t n,
+                            void *stream);
+
+/* robot/two_joint_robot.py:31-47  elbow_point()/end_effector() over arrays.
+ * out: [n][4] (elbow_x, elbow_y, ee_x, ee_y). */
+AG_API ag_status ag_forward_kinematics(const ag_params *p, const double *j1, const double *j2, double *out,
+                                int64_t n, void *stream);
+
+/* K2: scenario/scene_0.py:60-76  Scene.collision_check().  hit: [n] uint8; first_hit: optional
+ * [n] int32 = min(row*S+col) over all cells hit by either link, -1 if none. */
+AG_API ag_status ag_collision_check(const ag_params *p, const ag_grid *g, const double *j1, const double *j2,
+                             uint8_t *hit, int32_t *first_hit, int64_t n, int64_t env_id0,
+                             int32_t engine, void *stream);
+
+/* K1: scenario/scene_0.py:88-103  Scene.step(action).  j1,j2,reward,flags are in/out (sticky
+ * semantics).  actions: [n][2] float64 (actions_f32 == 0) or float32.  Optional outputs:
+ * ee [n][2] float64 end effector, dist [n][2] float64 (|tx-EEx|, |ty-EEy|), first_hit [n] int32. */
+AG_API ag_status ag_step(const ag_params *p, const ag_grid *g, double *j1, double *j2, const void *actions,
+                  int32_t actions_f32, float *reward, uint8_t *flags, double *ee, double *dist,
+                  int32_t *first_hit, int64_t *stats, int64_t n, int64_t env_id0, int32_t engine,
+                  void *stream);
+
+/* K3: scenario/scene_0.py:105-113,174-181  Scene.reset() / random_valid_pose() for envs with
+ * mask[e] != 0 (mask == NULL: all).  Candidates come from reset_u [n][R][2] float64 uniforms
+ * (consumed from reset_ctr[e]) or, when reset_u == NULL, from Philox stream 1 keyed by
+ * (seed, env_id0+e).  clear_flags != 0 -> reset() (clears reward/flags); 0 -> random_valid_pose(). */
+AG_API ag_status ag_reset(const ag_params *p, const ag_grid *g, double *j1, double *j2, float *reward,
+                   uint8_t *flags, uint32_t *reset_ctr, const uint8_t *mask, const double *reset_u,
+                   int32_t R, uint64_t seed, int32_t clear_flags, int64_t *stats, int64_t n,
+                   int64_t env_id0, int32_t engine, void *stream);
+
+/* K4: the rollout loop experiment/experiment_0.py:20-34 fused over K steps:
+ *   action -> step -> record -> if done|collision: reset.
+ * actions: [K][n][2] float32, or NULL = Philox stream 0 (float64 (u-0.5)*action_scale).
+ * reset_u: as ag_reset.  rec_*: [K][n] or all NULL (statistics only).
+ * stats: int64[AG_ST_COUNT], accumulated with one atomic per block per slot. */
+typedef struct ag_rollout_args {
+    int64_t n;
+    int64_t env_id0;
+    int32_t K;
+    int32_t engine;
+    uint64_t seed;
+    const float *actions;
+    const double *reset_u;
+    int32_t R;
+    int32_t reserved;
+    double *j1, *j2;
+    float *reward;
+    uint8_t *flags;
+    uint32_t *step_ctr, *reset_ctr, *ep_len;
+    float *rec_j1, *rec_j2, *rec_reward;
+    uint8_t *rec_flags;
+    int64_t *stats;
+} ag_rollout_args;
+
+AG_API ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream);
+
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+AG_API int64_t ag_launch_count(void);
+
+/* ---- host-buffer entry points (end-to-end path) -------------------------------------------- */
+
+/* Opaque pipelined executor: owns device staging buffers and streams for chunked
+ * H2D(actions) -> K4 -> D2H(records) with copies overlapping compute. */
+typedef struct ag_pipeline ag_pipeline;
+
+/* n envs resident on `device`, K steps per call, records enabled or not, chunk_envs per stage. */
+AG_API ag_status ag_pipeline_create(ag_pipeline **out, int32_t device, int64_t n, int32_t K,
+                             int64_t chunk_envs, int32_t record);
+AG_API void ag_pipeline_destroy(ag_pipeline *pl);
+/* Same as ag_rollout but actions / rec_* / stats_host are HOST pointers (pinned for full speed);
+ * env state pointers inside `a` stay DEVICE pointers (the state lives in HBM between calls).
+ * Returns after all records and stats are on the host. */
+AG_API ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g,
+                          const ag_rollout_args *a, int64_t *stats_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
