@@ -1,0 +1,409 @@
+"""GPU parity: the CUDA path (called through the C ABI via the Python host) against the CPU oracle
+and the committed reference goldens.
+
+Bar (BASELINE.json north_star): collision flags and first-hit cell indices bit-exact; joints,
+end-effector positions and rewards within 1e-5 relative (TOL below; observed ~1e-16).
+"""
+import hashlib
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5   # relative, north_star
+ENGINES = ["exact", "fast", "brute"]
+
+
+@pytest.fixture(scope="module")
+def ag():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import abstract_gym_b200 as ag
+    return ag
+
+
+@pytest.fixture(scope="module")
+def torch_():
+    import torch
+    return torch
+
+
+def rel_close(a, b, tol=TOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= tol * np.maximum(np.abs(b), 1e-3))
+
+
+def random_grid(rng, S, p):
+    occ = (rng.random((S, S)) < p).astype(np.uint8)
+    return occ
+
+
+def make_scene(ag, torch, occ_or_grid, j1, j2, **kw):
+    if isinstance(occ_or_grid, np.ndarray):
+        g = ag.OccupancyGrid(size=9, random_obstacle=False)
+        g.load_from_matrix(occ_or_grid)
+    else:
+        g = occ_or_grid
+    rb = ag.BatchedTwoJointRobot(torch.as_tensor(j1, device="cuda"), torch.as_tensor(j2, device="cuda"))
+    return ag.BatchedScene(rb, g, **kw)
+
+
+# ------------------------------------------------------------------ goldens from the reference
+
+def test_predicate_goldens(ag, golden_dir):
+    z = np.load(os.path.join(golden_dir, "predicate_cases.npz"))
+    out = ag.segment_square_arrays(z["seg"], z["sq"], want_abc=True, want_corner_values=True)
+    nan_ok = np.isnan(z["abc"]) & np.isnan(out["abc"])
+    assert np.all((out["abc"] == z["abc"]) | nan_ok)
+    assert np.array_equal(np.sign(out["v"]), z["signs"])
+    crash = z["out"] == 2
+    assert np.array_equal(out["hit"][~crash], z["out"][~crash] == 1)
+    assert out["axis_aligned"] == int(crash.sum())
+
+
+def test_fk_goldens(ag, golden_dir):
+    z = np.load(os.path.join(golden_dir, "fk_cases.npz"))
+    fk = ag.forward_kinematics(z["j"][:, 0], z["j"][:, 1]).cpu().numpy()
+    assert rel_close(fk, z["fk"])
+    assert np.abs(fk - z["fk"]).max() < 1e-14   # CUDA sincos vs glibc: a few ulp
+
+
+def test_collision_checker_main_block(ag):
+    c = ag.CollisionChecker(ag.Line(ag.Point(0, 0), ag.Point(1, 2)), ag.Square(ag.Point(0, 0.8), ag.Point(0.9, 1.4)))
+    assert c.collision_check() is True                      # utils/collision_checker.py:94-96
+    assert (c.a, c.b, c.c) == (1.0, -0.5, 0.0)
+    rb = ag.TwoJointRobot(0.3, 1.2)
+    assert rel_close([rb.end_effector().x, rb.end_effector().y], [0.4908419219932445, 0.39781980845470366], 1e-14)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["manual9", "rand9", "rand31", "rand64", "rand6", "matrix5"])
+def test_scene_step_goldens(ag, torch_, golden_dir, name, engine):
+    z = np.load(os.path.join(golden_dir, "scene_cases.npz"))
+    occ = z[name + "/occ"]
+    j0, acts, out, fh, ee = (z[name + "/" + k] for k in ("j0", "actions", "out", "first_hit", "ee"))
+    sc = make_scene(ag, torch_, occ, j0[:, 0], j0[:, 1], engine=engine)
+    for t in range(acts.shape[1]):
+        j1, j2, rw, done, coll, extra = sc.step(torch_.as_tensor(acts[:, t], device="cuda"), want_ee=True,
+                                                want_first_hit=(engine != "fast"))
+        assert np.array_equal(j1.cpu().numpy(), out[:, t, 0]) and np.array_equal(j2.cpu().numpy(), out[:, t, 1])
+        assert np.array_equal(rw.cpu().numpy().astype(np.float64), out[:, t, 2])
+        assert np.array_equal(done.cpu().numpy(), out[:, t, 3] != 0)
+        assert np.array_equal(coll.cpu().numpy(), out[:, t, 4] != 0)
+        assert rel_close(extra["ee"].cpu().numpy(), ee[:, t])
+        if engine != "fast":
+            hit_now, fh_now = sc.collision_check(first_hit=True)
+            assert np.array_equal(fh_now.cpu().numpy(), fh[:, t])
+            assert np.array_equal(extra["first_hit"].cpu().numpy(), fh[:, t])
+
+
+@pytest.mark.parametrize("engine", ["exact", "fast"])
+def test_reach_sequences(ag, torch_, golden_dir, engine):
+    z = np.load(os.path.join(golden_dir, "scene_cases.npz"))
+    start, seq = z["reach/start"], z["reach/seq"]
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    sc = make_scene(ag, torch_, g, start[:, 0], start[:, 1], engine=engine)
+    for t in range(seq.shape[1]):
+        j1, j2, rw, done, coll = sc.step(torch_.as_tensor(seq[:, t, 0:2].copy(), device="cuda"))
+        assert np.array_equal(j1.cpu().numpy(), seq[:, t, 2])
+        assert np.array_equal(rw.cpu().numpy().astype(np.float64), seq[:, t, 4])
+        assert np.array_equal(done.cpu().numpy(), seq[:, t, 5] != 0)
+        assert np.array_equal(coll.cpu().numpy(), seq[:, t, 6] != 0)
+    assert (seq[:, :, 5] != 0).any()
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_scene_dropin_reproduces_reference_digest(ag, golden_dir, idx):
+    """experiment/experiment_0.py:13-34 run through OUR Scene/TwoJointRobot/OccupancyGrid with the
+    reference's seed must give the reference's sha256 (SURVEY.md section 8c goldens)."""
+    g = json.load(open(os.path.join(golden_dir, "reference_goldens.json")))["experiment0"][idx]
+    steps = 6000 if idx else g["steps"]          # full 20 000 steps for seed 0, a prefix check for the others
+    np.random.seed(g["seed"])
+    rob = ag.TwoJointRobot(joint_1=1.0, joint_2=2.5)
+    occ = ag.OccupancyGrid(size=9, random_obstacle=False)
+    s = ag.Scene(robot=rob, env=occ, visualize=False)
+    s.random_valid_pose()
+    h = hashlib.sha256()
+    resets = []
+    for i in range(steps):
+        a = s.sample_action(scale_factor=0.1)
+        j1, j2, r, d, c = s.step(a)
+        h.update(struct.pack("<5d2B", j1, j2, a[0], a[1], r, d, c))
+        if i == 0:
+            assert [float(j1), float(j2), float(a[0]), float(a[1])] == g["first_record"][:4]
+        if d or c:
+            resets.append(i)
+            s.reset()
+    assert resets == [r for r in g["resets"] if r < steps]
+    if steps == g["steps"]:
+        assert h.hexdigest() == g["sha256"]
+        assert [float(rob.joint_1), float(rob.joint_2)] == g["final_joints"]
+
+
+# ------------------------------------------------------------------ config 2: 4096 envs, 1 step, vs oracle
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_config2_4096_envs_one_step(ag, torch_, oracle, engine):
+    rng = np.random.default_rng(42)
+    n = 4096
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = (rng.random((n, 2)) - 0.5) * 0.1
+    sq, ci = oracle.manual_grid()
+    o1, o2 = j1.copy(), j2.copy()
+    rw, fl = np.zeros(n), np.zeros(n, dtype=np.uint8)
+    ref = oracle.step_batch(o1, o2, acts, rw, fl, sq, ci)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    sc = make_scene(ag, torch_, g, j1, j2, engine=engine)
+    d1, d2, drw, ddone, dcoll, extra = sc.step(torch_.as_tensor(acts, device="cuda"), want_ee=True,
+                                               want_first_hit=(engine != "fast"))
+    assert np.array_equal(d1.cpu().numpy(), o1) and np.array_equal(d2.cpu().numpy(), o2)
+    assert np.array_equal(dcoll.cpu().numpy(), (fl & 1) != 0)          # bit-exact flags
+    assert np.array_equal(ddone.cpu().numpy(), (fl & 2) != 0)
+    assert np.array_equal(drw.cpu().numpy().astype(np.float64), rw)
+    assert rel_close(extra["ee"].cpu().numpy(), ref["ee"]) and rel_close(extra["dist"].cpu().numpy(), ref["dist"])
+    if engine != "fast":
+        assert np.array_equal(extra["first_hit"].cpu().numpy(), ref["first_hit"])   # bit-exact cell indices
+    assert 300 < int((fl & 1).sum()) < 800
+
+
+# ------------------------------------------------------------------ engines agree at scale (size-independent property)
+
+@pytest.mark.parametrize("S,p,n", [(9, None, 1 << 21), (9, 0.1, 1 << 20), (31, 0.01, 1 << 20), (6, 0.06, 1 << 19),
+                                   (64, 0.02, 1 << 20), (256, 0.008, 1 << 19), (1024, 0.002, 1 << 18)])
+def test_engines_agree_at_scale(ag, torch_, S, p, n):
+    """EXACT traversal == FAST filter == BRUTE (every occupied cell, the reference's loop) on millions
+    of uniform poses: 0 mismatches allowed."""
+    rng = np.random.default_rng(S * 1000 + 7)
+    if p is None:
+        g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    else:
+        g = ag.OccupancyGrid(size=9, random_obstacle=False)
+        g.load_from_matrix(random_grid(rng, S, p))
+    gen = torch_.Generator(device="cuda").manual_seed(S)
+    rb = ag.BatchedTwoJointRobot.random(n, device="cuda", generator=gen)
+    sc = ag.BatchedScene(rb, g)
+    hit_e, fh_e = sc.collision_check(first_hit=True, engine="exact")
+    hit_f = sc.collision_check(engine="fast")
+    nb = n if S <= 256 else 1 << 15
+    sc_b = ag.BatchedScene(ag.BatchedTwoJointRobot(rb.joint_1[:nb], rb.joint_2[:nb]), g)
+    hit_b, fh_b = sc_b.collision_check(first_hit=True, engine="brute")
+    assert int((hit_e != hit_f).sum().item()) == 0
+    assert int((hit_e[:nb] != hit_b).sum().item()) == 0
+    assert int((fh_e[:nb] != fh_b).sum().item()) == 0
+    frac = float(hit_e.float().mean().item())
+    assert 0.01 < frac < 0.99, frac
+
+
+@pytest.mark.parametrize("S,p", [(9, None), (31, 0.01), (256, 0.008)])
+def test_collision_vs_oracle_large(ag, torch_, oracle, S, p):
+    rng = np.random.default_rng(S + 1)
+    n = 200000 if S <= 31 else 20000
+    if p is None:
+        g = ag.OccupancyGrid(size=9, random_obstacle=False)
+        sq, ci = oracle.manual_grid()
+    else:
+        occ = random_grid(rng, S, p)
+        g = ag.OccupancyGrid(size=9, random_obstacle=False)
+        g.load_from_matrix(occ)
+        sq, ci = oracle.grid_squares(occ)
+    j1, j2 = rng.uniform(-10, 10, n), rng.uniform(-10, 10, n)
+    hit, fh, mg = oracle.collision_batch(j1, j2, sq, ci, want_margin=True)
+    sc = make_scene(ag, torch_, g, j1, j2)
+    for engine in ("exact", "fast"):
+        dh, dfh = sc.collision_check(first_hit=True, engine=engine)
+        bad = dh.cpu().numpy() != (hit != 0)
+        # north_star accounting: mismatches with an oracle decision margin < 1e-6 m are boundary-excused
+        hard = int((bad & (mg >= 1e-6)).sum())
+        assert hard == 0 and int(bad.sum()) == 0, (engine, int(bad.sum()), hard)
+        assert np.array_equal(dfh.cpu().numpy(), fh)
+
+
+# ------------------------------------------------------------------ K4 rollouts vs oracle
+
+def _rollout_case(ag, torch, oracle, occs, n, K, engine, scripted, envs_per_grid=None, seed=9, R=24, p_manual=False):
+    rng = np.random.default_rng(1000 + n + K)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    if p_manual:
+        grids_sq = [oracle.manual_grid()[0]]
+        g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    elif len(occs) == 1:
+        grids_sq = [oracle.grid_squares(occs[0])[0]]
+        g = ag.OccupancyGrid(size=9, random_obstacle=False)
+        g.load_from_matrix(occs[0])
+    else:
+        grids_sq = [oracle.grid_squares(o)[0] for o in occs]
+        g = ag.BatchedOccupancyGrid(torch.as_tensor(np.stack(occs), device="cuda"), envs_per_grid)
+    actions = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32) if scripted else None
+    reset_u = rng.random((n, R, 2)) if scripted else None
+    # oracle
+    st = oracle.RolloutState(j1, j2)
+    p = oracle.default_params()
+    rec, stats = oracle.rollout(st, K, grids_sq, envs_per_grid=envs_per_grid, env_id0=0, seed=seed,
+                                actions_f32=actions, reset_u=reset_u, params=p)
+    # device
+    sc = make_scene(ag, torch, g, j1, j2, engine=engine, seed=seed)
+    drec = sc.rollout(K, actions=None if actions is None else torch.as_tensor(actions, device="cuda"),
+                      reset_u=None if reset_u is None else torch.as_tensor(reset_u, device="cuda"))
+    torch.cuda.synchronize()
+    assert np.array_equal(drec["flags"].cpu().numpy(), rec["flags"])
+    assert np.array_equal(drec["reward"].cpu().numpy(), rec["reward"])
+    assert np.array_equal(drec["j1"].cpu().numpy(), rec["j1"]) and np.array_equal(drec["j2"].cpu().numpy(), rec["j2"])
+    assert np.array_equal(sc.robot.joint_1.cpu().numpy(), st.j1) and np.array_equal(sc.robot.joint_2.cpu().numpy(), st.j2)
+    assert np.array_equal(sc.step_ctr.cpu().numpy().view(np.uint32), st.step_ctr)
+    assert np.array_equal(sc.reset_ctr.cpu().numpy().view(np.uint32), st.reset_ctr)
+    assert np.array_equal(sc.ep_len.cpu().numpy().view(np.uint32), st.ep_len)
+    assert np.array_equal(sc.flags.cpu().numpy(), st.flags)
+    assert np.array_equal(sc.stats.cpu().numpy(), stats)
+    return stats
+
+
+@pytest.mark.parametrize("engine", ["exact", "fast"])
+@pytest.mark.parametrize("scripted", [True, False])
+def test_rollout_scene0_vs_oracle(ag, torch_, oracle, engine, scripted):
+    stats = _rollout_case(ag, torch_, oracle, None, 4096, 64, engine, scripted, p_manual=True)
+    assert stats[oracle.ST_ENV_STEPS] == 4096 * 64 and stats[oracle.ST_EPISODES] > 100
+
+
+@pytest.mark.parametrize("engine", ["exact", "fast"])
+def test_rollout_ragged_and_tiny(ag, torch_, oracle, engine):
+    for n, K in ((1, 5), (31, 3), (257, 17), (1000, 1)):
+        _rollout_case(ag, torch_, oracle, None, n, K, engine, True, p_manual=True)
+
+
+@pytest.mark.parametrize("engine", ["exact", "fast"])
+def test_rollout_config4_highres_grid(ag, torch_, oracle, engine):
+    rng = np.random.default_rng(4)
+    occ = random_grid(rng, 1024, 0.002)
+    stats = _rollout_case(ag, torch_, oracle, [occ], 1024, 8, engine, False, seed=3)
+    assert stats[oracle.ST_EPISODES] > 0
+
+
+@pytest.mark.parametrize("engine", ["exact", "fast"])
+def test_rollout_config5_heterogeneous_grids(ag, torch_, oracle, engine):
+    rng = np.random.default_rng(5)
+    occs = [random_grid(rng, 256, 0.008) for _ in range(8)]
+    stats = _rollout_case(ag, torch_, oracle, occs, 2048, 16, engine, False, envs_per_grid=256, seed=11)
+    assert stats[oracle.ST_EPISODES] > 0
+    # envs_per_grid not a multiple of the block: per-thread grid lookup path
+    _rollout_case(ag, torch_, oracle, occs[:3], 900, 6, engine, True, envs_per_grid=100, seed=12)
+
+
+def test_rollout_dense_grid_counts_stuck_resets(ag, torch_, oracle):
+    rng = np.random.default_rng(6)
+    occ = random_grid(rng, 31, 0.5)          # almost no free pose: bounded rejection sampling gives up and counts
+    stats = _rollout_case(ag, torch_, oracle, [occ], 512, 4, "fast", False, seed=2)
+    assert stats[oracle.ST_STUCK_RESETS] > 0
+
+
+def test_empty_grid_never_collides(ag, torch_):
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    g.load_from_matrix(np.zeros((9, 9)))     # the reference raises ValueError here (occupancy_grid.py:64)
+    rb = ag.BatchedTwoJointRobot.random(10000, device="cuda")
+    sc = ag.BatchedScene(rb, g)
+    for e in ENGINES:
+        assert int(sc.collision_check(engine=e).sum().item()) == 0
+    sc.rollout(8, record=False)
+    st = sc.stats_dict()
+    assert st["collisions"] == 0 and st["env_steps"] == 80000
+
+
+# ------------------------------------------------------------------ K3 / K5 / pipeline / sharding
+
+def test_reset_kernel_vs_reference_semantics(ag, torch_, oracle):
+    rng = np.random.default_rng(8)
+    n, R = 5000, 16
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    u = rng.random((n, R, 2))
+    sq, ci = oracle.manual_grid()
+    hit, _, _ = oracle.collision_batch(j1, j2, sq, ci)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    sc = make_scene(ag, torch_, g, j1, j2)
+    sc.flags.fill_(3); sc.step_reward.fill_(-1000.0)
+    mask = (np.arange(n) % 3 != 0)
+    sc.reset(mask=torch_.as_tensor(mask, device="cuda"), reset_u=torch_.as_tensor(u, device="cuda"))
+    d1, d2 = sc.robot.joint_1.cpu().numpy(), sc.robot.joint_2.cpu().numpy()
+    rc = sc.reset_ctr.cpu().numpy()
+    # expected: scene_0.py:179-181 -- resample only while colliding, candidates in order, (u*pi)*2.0
+    e1, e2, erc = j1.copy(), j2.copy(), np.zeros(n, dtype=np.int32)
+    for e in np.nonzero(mask & (hit != 0))[0]:
+        k = 0
+        while True:
+            e1[e], e2[e] = u[e, k, 0] * np.pi * 2.0, u[e, k, 1] * np.pi * 2.0
+            k += 1
+            if not oracle.collision_batch(e1[e:e + 1], e2[e:e + 1], sq, ci)[0][0]:
+                break
+        erc[e] = k
+    assert np.array_equal(d1, e1) and np.array_equal(d2, e2) and np.array_equal(rc, erc)
+    fl = sc.flags.cpu().numpy()
+    assert np.all(fl[mask] == 0) and np.all(fl[~mask] == 3)      # a non-colliding pose is kept, flags cleared
+    assert int(sc.collision_check().cpu().numpy()[mask].sum()) == 0
+
+
+def test_device_grid_pack_matches_host(ag, torch_):
+    rng = np.random.default_rng(9)
+    for S in (5, 9, 33, 256):
+        occ = (rng.random((3, S, S)) < 0.2).astype(np.uint8)
+        dg = ag.DeviceGrid.from_device_matrices(torch_.as_tensor(occ, device="cuda"))
+        assert np.array_equal(dg.unpack(), occ)
+        hg = ag.DeviceGrid.from_host_matrix(occ[1], device="cuda")
+        assert np.array_equal(hg.unpack()[0], occ[1])
+
+
+def test_rollout_host_pipeline_equals_device_rollout(ag, torch_):
+    n, K = 5000, 12
+    rng = np.random.default_rng(10)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    a = make_scene(ag, torch_, g, j1, j2, seed=4)
+    b = make_scene(ag, torch_, g, j1, j2, seed=4)
+    ra = a.rollout(K, actions=torch_.as_tensor(acts, device="cuda"))
+    hact = torch_.as_tensor(acts).pin_memory()
+    out = b.alloc_records(K, pinned_host=True)
+    st = b.rollout_host(K, hact, out, chunk_envs=1024)
+    for k in ("j1", "j2", "reward", "flags"):
+        assert np.array_equal(ra[k].cpu().numpy(), out[k].numpy()), k
+    assert np.array_equal(a.robot.joint_1.cpu().numpy(), b.robot.joint_1.cpu().numpy())
+    assert a.stats_dict() == b.stats_dict() == st
+    # statistics-only, in-kernel actions
+    a.rollout(K, record=False); b.rollout_host(K, None, None, chunk_envs=2048)
+    assert a.stats_dict() == b.stats_dict()
+    assert np.array_equal(a.robot.joint_2.cpu().numpy(), b.robot.joint_2.cpu().numpy())
+
+
+def test_shard_invariance_on_device(ag, torch_):
+    """two shards with global env ids == one launch over all envs (Philox keyed by global id)"""
+    n, K = 6000, 20
+    rng = np.random.default_rng(11)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    occs = np.stack([random_grid(rng, 64, 0.02) for _ in range(6)])
+    g = ag.BatchedOccupancyGrid(torch_.as_tensor(occs, device="cuda"), envs_per_grid=512)
+    full = make_scene(ag, torch_, g, j1, j2, seed=21)
+    rf = full.rollout(K)
+    from abstract_gym_b200.sharding import shard_range
+    tot = torch_.zeros_like(full.stats)
+    for r in range(3):
+        lo, hi = shard_range(n, r, 3)
+        sh = make_scene(ag, torch_, g, j1[lo:hi], j2[lo:hi], seed=21, env_id0=lo)
+        rs = sh.rollout(K)
+        assert torch_.equal(rs["flags"], rf["flags"][:, lo:hi]) and torch_.equal(rs["j1"], rf["j1"][:, lo:hi])
+        tot += sh.stats
+    assert torch_.equal(tot, full.stats)
+
+
+def test_fast_fk_error_budget(ag, torch_):
+    """the float32 FK of the FAST engine stays inside AG_DELTA_P = 3e-7 m of the float64 FK;
+    checked indirectly: FAST == EXACT on 2^22 poses of a dense-ish grid (0 mismatches)"""
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    rng = np.random.default_rng(12)
+    g.load_from_matrix(random_grid(rng, 48, 0.05))
+    gen = torch_.Generator(device="cuda").manual_seed(99)
+    u = torch_.rand(2, 1 << 22, dtype=torch_.float64, device="cuda", generator=gen)
+    rb = ag.BatchedTwoJointRobot((u[0] - 0.5) * 2000.0, (u[1] - 0.5) * 2000.0)     # |j| up to 1000 rad
+    sc = ag.BatchedScene(rb, g)
+    assert int((sc.collision_check(engine="exact") != sc.collision_check(engine="fast")).sum().item()) == 0
