@@ -1,30 +1,53 @@
 // ag_fast.cuh -- FAST engine: float32 interval filter in front of the float64 reference predicate.
 //
-// Idea (exact-predicate style): every decision of the step (corner sign test, entry/exit lambda
-// test, reach test) is first evaluated in float32 together with a rigorous bound on how far the
-// float32 value can be from the real-arithmetic value of the float64 inputs.  If every decision
-// clears its bound the float32 answer IS the reference's answer (the reference's own float64
-// rounding is ~1e-16, eight orders of magnitude below the filter bounds); otherwise the lane is
-// "undecided" and re-evaluated by the EXACT engine.  The result is therefore identical to EXACT
-// by construction; tests/test_gpu_parity.py checks it on 10^8+ poses.
+// Idea (exact-predicate style): every decision of a step (does link L hit cell C, is the target
+// reached) is first evaluated in float32 together with a bound on how far the float32 quantities
+// can be from the real-arithmetic values of the float64 inputs.  A decision that clears its bound
+// IS the reference's decision (the reference's own float64 rounding noise is orders of magnitude
+// below the bounds, except for nearly axis-aligned links, which the filter refuses to decide);
+// anything else is "undecided" and re-evaluated by the EXACT engine.  FAST == EXACT by
+// construction; tests/test_gpu_parity.py checks it on >10^7 poses per grid class.
 //
-// Error budget (metres unless noted), scene_0-class geometry (|coordinates| <= ~2):
-//   FK:   quarter-turn reduction in float64, minimax sin/cos polynomials in float32:
-//         |sin,cos error| <= 1.4e-7  ->  elbow/EE coordinates within AG_DELTA_P = 3e-7.
-//   corners: (float)min_x[c] and +side: <= 1.0e-7 (AG_DELTA_C).
+// Real-arithmetic restatement of utils/collision_checker.py:34-85 used by the filter (derivation
+// in DESIGN.md "FAST engine"):  with cr_ij = (X_i-p0x)*dy - (Y_j-p0y)*dx,
+//     hit  <=>  P2 and OVL and not B
+//     P2  : some cr > 0 and some cr < 0          (line strictly separates the corners, :41-43)
+//     OVL : the open x- and y-ranges of the segment overlap the square's   (t_in < 1, t_out > eps)
+//     B   : both end points lie in the closed square                       (t_in <= eps, t_out >= 1)
+// No division appears, so no error amplification for shallow links.
+//
+// Error budget (metres), scene_0-class geometry (|coordinates| < 2, links < 1):
+//   AG_DELTA_P  float32 FK coordinate vs float64 FK coordinate      <= 3.0e-7 (measured 1.8e-7)
+//   AG_DELTA_C  float32 corner (and +side) vs float64 corner        <= 1.5e-7
+//   AG_M        any difference of a link coordinate and a corner    <= 8.0e-7  (delta_p+delta_c+rounding)
 #pragma once
 #include "ag_device.cuh"
 
 namespace agd {
 
-constexpr float AG_DELTA_P = 3.0e-7f;    // |float32 FK coordinate - float64 FK coordinate|
-constexpr float AG_DELTA_C = 1.5e-7f;    // |float32 corner - float64 corner|
+constexpr float AG_DELTA_P = 3.0e-7f;
+constexpr float AG_DELTA_C = 1.5e-7f;
+constexpr float AG_M = 8.0e-7f;          // margin on (link coordinate - corner) comparisons
+constexpr float AG_K1 = 1.2e-6f;         // cross-product error coefficient (see narrow_f32)
 constexpr float AG_MIN_DXY = 1.0e-5f;    // below this |dx| or |dy| the filter refuses to decide
+constexpr int AG_LIST_MAX = 8;           // obstacle-list broad phase for grids with <= 8 occupied cells
 
 struct ArmF { float ex, ey, gx, gy; };
 
-// sin(pi/2*f), cos(pi/2*f) for f in [-0.5, 0.5] (quarter turns); max abs error 9e-8 (host-checked,
-// see DESIGN.md "FAST engine error budget").
+// per-thread float32 constants, hoisted out of the step loop
+struct FastConst {
+    float l1, l2, side, half, inv_side, tx, ty, reach_eps;
+};
+__device__ __forceinline__ FastConst make_fast_const(const ag_params &P, const GridDev &G) {
+    FastConst C;
+    C.l1 = (float)P.link_1; C.l2 = (float)P.link_2;
+    C.side = (float)G.side; C.half = (float)G.half; C.inv_side = (float)G.inv_side;
+    C.tx = (float)P.target_x; C.ty = (float)P.target_y; C.reach_eps = (float)P.reach_eps;
+    return C;
+}
+
+// sin(pi/2*f), cos(pi/2*f) for f in [-0.5, 0.5] (quarter turns); max abs error 9e-8
+// (near-minimax fits, checked against float64 on 2e6 points: DESIGN.md "FAST engine error budget").
 __device__ __forceinline__ void sincos_quarter(float f, float &s, float &c) {
     const float u = f * f;
     float ps = -0.0046021631049598674f;
@@ -40,110 +63,172 @@ __device__ __forceinline__ void sincos_quarter(float f, float &s, float &c) {
 }
 
 // float32 sin/cos of a float64 angle: j*(2/pi) and the rounding to the nearest quarter turn stay
-// in float64 (3 DP ops), the rest is float32.  ok=false for |j| beyond the range where the
-// float64 reduction is trustworthy.
-__device__ __forceinline__ void sincos_f32_of_f64(double j, float &s, float &c, bool &ok) {
+// in float64 (4 DP ops), the rest is float32.
+__device__ __forceinline__ void sincos_f32_of_f64(double j, float &s, float &c) {
     const double t = j * 0.63661977236758134308;               // quarter turns
     const double tk = t + 6755399441055744.0;                  // 1.5*2^52: rounds to nearest integer
     const int k = __double2loint(tk);
     const float f = (float)(t - (tk - 6755399441055744.0));
-    ok = ok && (fabs(j) < 1.0e6);
     float sq, cq;
     sincos_quarter(f, sq, cq);
-    const float a = (k & 1) ? cq : sq, b = (k & 1) ? sq : cq;  // q=1,3 swap
+    const float a = (k & 1) ? cq : sq, b = (k & 1) ? sq : cq;  // odd quadrant: swap
     s = (k & 2) ? -a : a;                                      // q: 0:(s,c) 1:(c,-s) 2:(-s,-c) 3:(-c,s)
     c = ((k + 1) & 2) ? -b : b;
 }
 
-__device__ __forceinline__ ArmF fast_forward_kinematics(double j1, double j2, float l1, float l2, bool &ok) {
+// ok=false when an angle is outside the range where the reduction above is trustworthy
+__device__ __forceinline__ ArmF fast_forward_kinematics(double j1, double j2, const FastConst &C, bool &ok) {
     float s1, c1, s2, c2;
-    sincos_f32_of_f64(j1, s1, c1, ok);
-    sincos_f32_of_f64(j2, s2, c2, ok);
+    sincos_f32_of_f64(j1, s1, c1);
+    sincos_f32_of_f64(j2, s2, c2);
+    // |j| < 2^20 rad, tested on the exponent fields (no float64 compare in the hot loop)
+    ok = (max(__double2hiint(j1) & 0x7FF00000, __double2hiint(j2) & 0x7FF00000) < ((1023 + 20) << 20));
     ArmF a;
-    a.ex = c1 * l1; a.ey = s1 * l1;
-    a.gx = fmaf(c2, l2, a.ex); a.gy = fmaf(s2, l2, a.ey);
+    a.ex = c1 * C.l1; a.ey = s1 * C.l1;
+    a.gx = fmaf(c2, C.l2, a.ex); a.gy = fmaf(s2, C.l2, a.ey);
     return a;
 }
 
 // ---------------------------------------------------------------- narrow phase, one (link, cell)
 // returns 0 = certainly no hit, 1 = certainly hit, 2 = undecided.
-// Real-arithmetic restatement of utils/collision_checker.py:34-85: with
-//   cr_ij = (X_i - p0x)*dy - (Y_j - p0y)*dx           (sign(v_ij) = sign(cr_ij)*sign(dx*dy))
-//   t_in = max(min(tx0,tx1), min(ty0,ty1)), t_out = min(max(tx0,tx1), max(ty0,ty1)),
-//   tx_i = (X_i - p0x)/dx, ty_j = (Y_j - p0y)/dy
-// the reference returns  (some cr > 0 and some cr < 0) and (eps < t_in < 1 or eps < t_out < 1).
-struct LinkF { float p0x, p0y, dx, dy, rdx, rdy, et; bool degenerate; };
+struct LinkF {
+    float p0x, p0y, dx, dy, xlo, xhi, ylo, yhi, ecr;
+    bool degenerate;
+};
 
-__device__ __forceinline__ LinkF make_link_f(float p0x, float p0y, float p1x, float p1y) {
+__device__ __forceinline__ LinkF make_link_f(float p0x, float p0y, float p1x, float p1y, float side) {
     LinkF L;
     L.p0x = p0x; L.p0y = p0y; L.dx = p1x - p0x; L.dy = p1y - p0y;
+    L.xlo = fminf(p0x, p1x); L.xhi = fmaxf(p0x, p1x); L.ylo = fminf(p0y, p1y); L.yhi = fmaxf(p0y, p1y);
+    // |error of cr| <= (delta_d + 2^-23)*(|ux|+|uy|) + delta_u*(|dx|+|dy|) with delta_d = 6.4e-7, delta_u = 5.5e-7;
+    // for a candidate cell (ranges overlap within AG_M) |ux| <= |dx| + side + AG_M, same for y.
+    L.ecr = AG_K1 * (2.0f * (fabsf(L.dx) + fabsf(L.dy)) + 2.02f * side + 4.0e-6f);
     L.degenerate = fminf(fabsf(L.dx), fabsf(L.dy)) < AG_MIN_DXY;
-    L.rdx = __frcp_rn(L.dx); L.rdy = __frcp_rn(L.dy);
-    // |t error| for |t| <= 2 (clamped): numerator error + |t| * denominator error, both <= K2
-    const float K2 = 2.0f * AG_DELTA_P + AG_DELTA_C + 2.4e-7f;
-    L.et = 3.0f * K2 * fmaxf(fabsf(L.rdx), fabsf(L.rdy)) + 1.0e-6f;
     return L;
 }
 
-__device__ __forceinline__ int narrow_f32(const LinkF &L, float min_x, float min_y, float side) {
-    if (L.degenerate) return 2;
-    const float ux0 = min_x - L.p0x, ux1 = (min_x + side) - L.p0x;
-    const float uy0 = min_y - L.p0y, uy1 = (min_y + side) - L.p0y;
-    // corner sign test
+__device__ __forceinline__ int narrow_f32(const LinkF &L, float min_x, float min_y, float max_x, float max_y) {
+    // corner sign test: max/min over the four cross products
+    const float ux0 = min_x - L.p0x, ux1 = max_x - L.p0x, uy0 = min_y - L.p0y, uy1 = max_y - L.p0y;
     const float a0 = ux0 * L.dy, a1 = ux1 * L.dy, b0 = uy0 * L.dx, b1 = uy1 * L.dx;
-    const float c00 = a0 - b0, c01 = a0 - b1, c10 = a1 - b0, c11 = a1 - b1;
-    const float K1 = 2.0f * AG_DELTA_P + AG_DELTA_C + 3.6e-7f;
-    const float ecr = K1 * (fmaxf(fabsf(ux0), fabsf(ux1)) + fmaxf(fabsf(uy0), fabsf(uy1)) + fabsf(L.dx) + fabsf(L.dy));
-    const float cmax = fmaxf(fmaxf(c00, c01), fmaxf(c10, c11)), cmin = fminf(fminf(c00, c01), fminf(c10, c11));
-    const bool pos = cmax > ecr, neg = cmin < -ecr;
-    if (!(pos && neg)) {
-        // all four certainly on one side (or exactly... never: a zero is inside the band) -> miss
-        const bool all_certain = fminf(fminf(fabsf(c00), fabsf(c01)), fminf(fabsf(c10), fabsf(c11))) > ecr;
-        return all_certain ? 0 : 2;
-    }
-    // entry / exit parameters, clamped to [-1, 2] (monotone, 1-Lipschitz; thresholds 0 and 1 inside)
-    const float tx0 = fminf(fmaxf(ux0 * L.rdx, -1.0f), 2.0f), tx1 = fminf(fmaxf(ux1 * L.rdx, -1.0f), 2.0f);
-    const float ty0 = fminf(fmaxf(uy0 * L.rdy, -1.0f), 2.0f), ty1 = fminf(fmaxf(uy1 * L.rdy, -1.0f), 2.0f);
-    const float t_in = fmaxf(fminf(tx0, tx1), fminf(ty0, ty1));
-    const float t_out = fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1));
-    const float e = 1.01f * L.et;   // strictly above the bound, so t > e implies real t > section_eps (1e-10)
-    const bool in_sure = (t_in > e) && (t_in < 1.0f - e), out_sure = (t_out > e) && (t_out < 1.0f - e);
-    if (in_sure || out_sure) return 1;
-    const bool in_out = (t_in < -e) || (t_in > 1.0f + e), out_out = (t_out < -e) || (t_out > 1.0f + e);
-    return (in_out && out_out) ? 0 : 2;
+    const float cmax = fmaxf(a0, a1) - fminf(b0, b1), cmin = fminf(a0, a1) - fmaxf(b0, b1);
+    if (!((cmax > -L.ecr) && (cmin < L.ecr))) return 0;   // the line certainly misses the open square
+    // A nearly axis-aligned link: the reference switches formulas at exactly dx == 0 / dy == 0 and
+    // its lambda arithmetic gets noisy below |dx| ~ 1e-9; leave every such case to the EXACT engine.
+    if (L.degenerate) return 2;
+    // OVL / B from eight differences
+    const float a_min = fminf(fminf(L.xhi - min_x, max_x - L.xlo), fminf(L.yhi - min_y, max_y - L.ylo));
+    const float b_min = fminf(fminf(L.xlo - min_x, max_x - L.xhi), fminf(L.ylo - min_y, max_y - L.yhi));
+    if (!(a_min > -AG_M) || b_min > AG_M) return 0;       // ranges certainly disjoint, or segment wholly inside
+    const bool p2_certain = (cmax > L.ecr) && (cmin < -L.ecr);
+    return (p2_certain && (a_min > AG_M) && (b_min < -AG_M)) ? 1 : 2;
 }
 
-// ---------------------------------------------------------------- broad phase + narrow phase, one link
-// conservative float32 traversal of the bit grid (same scheme as link_exact, wider margins)
-__device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, float p0x, float p0y, float p1x,
-                                         float p1y) {
-    const float side = (float)G.side, half = (float)G.half, inv_side = (float)G.inv_side;
-    const float m = fmaxf(2.0e-6f, 1.0e-3f * side);
-    const float Sf = (float)G.S;
-    // rows: r = floor((half - y)/side) + 1
-    float rf_lo = floorf((half - (fmaxf(p0y, p1y) + m)) * inv_side) + 1.0f;
-    float rf_hi = floorf((half - (fminf(p0y, p1y) - m)) * inv_side) + 1.0f;
-    if (rf_lo > Sf - 1.0f || rf_hi < 0.0f) return 0;
-    const int r_lo = (int)fmaxf(rf_lo, 0.0f), r_hi = (int)fminf(rf_hi, Sf - 1.0f);
+// ---------------------------------------------------------------- obstacle-list broad phase (<= AG_LIST_MAX cells)
+// Built per block in shared memory from the staged bit grid, row-major order.
+struct FastList {
+    int m;                          // number of occupied cells, or -1 if the list form does not apply
+    float4 sq[AG_LIST_MAX];         // (min_x, min_y, max_x, max_y) as float32
+};
+
+// warp 0 builds the list (S <= 32: one row word per lane)
+__device__ __forceinline__ void build_fast_list(const GridDev &G, const GridView &V, FastList *fl) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int m = -1;
+        if (G.S <= 32) {
+            const uint32_t word = lane < G.S ? V.bits[lane] : 0u;
+            int cnt = __popc(word), pre = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, pre, o);
+                if (lane >= o) pre += v;
+            }
+            const int total = __shfl_sync(0xFFFFFFFFu, pre, 31);
+            if (total <= AG_LIST_MAX) {
+                m = total;
+                int slot = pre - cnt;
+                uint32_t w = word;
+                const float side = (float)G.side;
+                while (w) {
+                    const int c = __ffs(w) - 1;
+                    w &= w - 1;
+                    const float mnx = (float)V.min_x[c], mny = (float)V.min_y[lane];
+                    fl->sq[slot++] = make_float4(mnx, mny, mnx + side, mny + side);
+                }
+            }
+        }
+        if (lane == 0) fl->m = m;
+    }
+    __syncthreads();
+}
+
+// 0 / 1 certain, 2 undecided.  Warp-uniform loop over the (few) obstacles: range-overlap tests
+// for both links, then the narrow phase on the surviving (link, cell) pairs.
+__device__ __forceinline__ int arm_fast_list(const FastList *fl, const ArmF &a, const FastConst &C) {
+    const int m = fl->m;
+    const float x1lo = fminf(0.0f, a.ex), x1hi = fmaxf(0.0f, a.ex), y1lo = fminf(0.0f, a.ey), y1hi = fmaxf(0.0f, a.ey);
+    const float x2lo = fminf(a.ex, a.gx), x2hi = fmaxf(a.ex, a.gx), y2lo = fminf(a.ey, a.gy), y2hi = fmaxf(a.ey, a.gy);
+    uint32_t cand = 0;
+    for (int k = 0; k < m; ++k) {
+        const float4 q = fl->sq[k];
+        const bool o1 = (x1hi - q.x > -AG_M) && (q.z - x1lo > -AG_M) && (y1hi - q.y > -AG_M) && (q.w - y1lo > -AG_M);
+        const bool o2 = (x2hi - q.x > -AG_M) && (q.z - x2lo > -AG_M) && (y2hi - q.y > -AG_M) && (q.w - y2lo > -AG_M);
+        cand |= (o1 ? 1u : 0u) << (2 * k) | (o2 ? 2u : 0u) << (2 * k);
+    }
+    int result = 0;
+    if (cand) {
+        const LinkF L1 = make_link_f(0.0f, 0.0f, a.ex, a.ey, C.side);
+        const LinkF L2 = make_link_f(a.ex, a.ey, a.gx, a.gy, C.side);
+        while (cand) {
+            const int b = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float4 q = fl->sq[b >> 1];
+            const int v = narrow_f32((b & 1) ? L2 : L1, q.x, q.y, q.z, q.w);
+            if (v == 1) return 1;
+            result |= v;
+        }
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------- traversal broad phase (any grid), one link
+// conservative float32 traversal of the bit grid (same scheme as link_exact, wider margins).
+// floor() is replaced by a round-to-nearest magic-number add biased so that the low index can
+// only come out lower and the high index only higher (no F2I/FRND on the XU pipe).
+__device__ __forceinline__ int round_magic(float v) { return __float_as_int(v + 12582912.0f) - 0x4B400000; }
+
+__device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, const FastConst &C, float p0x, float p0y,
+                                         float p1x, float p1y) {
+    const float mcell = fmaxf(2.0e-6f * C.inv_side, 1.0e-3f) + 0.001f;   // margin in cells
+    const int S1 = G.S - 1;
+    const float ylo = fminf(p0y, p1y), yhi = fmaxf(p0y, p1y);
+    // row of y: floor((half - y)/side) + 1 ; low row from yhi, high row from ylo
+    int r_lo = round_magic(fmaf(-yhi, C.inv_side, C.half * C.inv_side + 0.5f - mcell));
+    int r_hi = round_magic(fmaf(-ylo, C.inv_side, C.half * C.inv_side + 0.5f + mcell));
+    if (r_lo > S1 || r_hi < 0) return 0;
+    r_lo = max(r_lo, 0); r_hi = min(r_hi, S1);
     const float dx = p1x - p0x, dy = p1y - p0y;
     const bool clip = (r_hi - r_lo >= 2) && (fabsf(dy) * 64.0f >= fabsf(dx));
     const float inv_dy = clip ? __frcp_rn(dy) : 0.0f;
-    const float mx = clip ? m + 5.0e-5f : m;
+    const float mxcell = clip ? mcell + 5.0e-5f * C.inv_side : mcell;
+    const float xoff = C.half * C.inv_side - 0.5f;
     int result = 0;
     bool have_link = false;
     LinkF L;
-    for (int r = r_lo; r <= r_hi; ++r) {
+    float yb = C.half - (float)r_lo * C.side;       // bottom edge of row r
+    for (int r = r_lo; r <= r_hi; ++r, yb -= C.side) {
         float xa = p0x, xb = p1x;
         if (clip) {
-            const float yb = half - (float)r * side - m, yt = half - (float)(r - 1) * side + m;
-            const float t0 = (yb - p0y) * inv_dy, t1 = (yt - p0y) * inv_dy;
+            const float m = mcell * C.side;
+            const float t0 = (yb - m - p0y) * inv_dy, t1 = (yb + C.side + m - p0y) * inv_dy;
             const float ta = __saturatef(fminf(t0, t1)), tb = __saturatef(fmaxf(t0, t1));
             xa = fmaf(ta, dx, p0x); xb = fmaf(tb, dx, p0x);
         }
-        const float cf_lo = floorf((fminf(xa, xb) - mx + half) * inv_side);
-        const float cf_hi = floorf((fmaxf(xa, xb) + mx + half) * inv_side);
-        if (cf_lo > Sf - 1.0f || cf_hi < 0.0f) continue;
-        const int c_lo = (int)fmaxf(cf_lo, 0.0f), c_hi = (int)fminf(cf_hi, Sf - 1.0f);
+        int c_lo = round_magic(fmaf(fminf(xa, xb), C.inv_side, xoff - mxcell));
+        int c_hi = round_magic(fmaf(fmaxf(xa, xb), C.inv_side, xoff + mxcell));
+        if (c_lo > S1 || c_hi < 0) continue;
+        c_lo = max(c_lo, 0); c_hi = min(c_hi, S1);
         for (int w = c_lo >> 5; w <= (c_hi >> 5); ++w) {
             uint32_t mask = 0xFFFFFFFFu;
             if (w == (c_lo >> 5)) mask &= 0xFFFFFFFFu << (c_lo & 31);
@@ -152,8 +237,9 @@ __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, fl
             while (word) {
                 const int c = (w << 5) + __ffs(word) - 1;
                 word &= word - 1;
-                if (!have_link) { L = make_link_f(p0x, p0y, p1x, p1y); have_link = true; }
-                const int v = narrow_f32(L, (float)V.min_x[c], (float)V.min_y[r], side);
+                if (!have_link) { L = make_link_f(p0x, p0y, p1x, p1y, C.side); have_link = true; }
+                const float mnx = (float)V.min_x[c], mny = (float)V.min_y[r];
+                const int v = narrow_f32(L, mnx, mny, mnx + C.side, mny + C.side);
                 if (v == 1) return 1;
                 result |= v;          // 0 or 2
             }
@@ -162,72 +248,78 @@ __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, fl
     return result;
 }
 
+// broad-phase selection: a compile-time choice for the rollout kernel (keeps its register
+// allocation small), a run-time one (BP_ANY) for K1..K3
+enum { BP_ANY = 0, BP_LIST = 1, BP_TRAVERSAL = 2 };
+
 // 0 / 1 certain, 2 undecided
-__device__ __forceinline__ int arm_fast(const GridDev &G, const GridView &V, const ArmF &a) {
-    const int v1 = link_fast(G, V, 0.0f, 0.0f, a.ex, a.ey);
+template <int BP>
+__device__ __forceinline__ int arm_fast(const GridDev &G, const GridView &V, const FastList *fl, const FastConst &C,
+                                        const ArmF &a) {
+    if (BP == BP_LIST) return (fl != nullptr && fl->m >= 0) ? arm_fast_list(fl, a, C) : 2;
+    if (BP == BP_ANY && fl != nullptr && fl->m >= 0) return arm_fast_list(fl, a, C);
+    const int v1 = link_fast(G, V, C, 0.0f, 0.0f, a.ex, a.ey);
     if (v1 == 1) return 1;
-    const int v2 = link_fast(G, V, a.ex, a.ey, a.gx, a.gy);
+    const int v2 = link_fast(G, V, C, a.ex, a.ey, a.gx, a.gy);
     if (v2 == 1) return 1;
     return v1 | v2;
 }
 
 // reach test filter, scenario/scene_0.py:129-130 ; 0/1 certain, 2 undecided
-__device__ __forceinline__ int reach_fast(const ag_params &P, const ArmF &a) {
-    const float eps = (float)P.reach_eps, m = AG_DELTA_P + 2.0e-7f;
-    const float ax = fabsf((float)P.target_x - a.gx), ay = fabsf((float)P.target_y - a.gy);
-    if (ax > eps + m || ay > eps + m) return 0;
-    if (ax < eps - m && ay < eps - m) return 1;
+__device__ __forceinline__ int reach_fast(const FastConst &C, const ArmF &a) {
+    const float m = AG_DELTA_P + 2.0e-7f;
+    const float worst = fmaxf(fabsf(C.tx - a.gx), fabsf(C.ty - a.gy));    // reached <=> worst < eps
+    if (worst > C.reach_eps + m) return 0;
+    if (worst < C.reach_eps - m) return 1;
     return 2;
 }
 
-// FAST collision_check of a pose (K2/K3): float32 first, EXACT for undecided lanes.
-__device__ __forceinline__ bool fast_pose_collides(const ag_params &P, const GridDev &G, const GridView &V, double j1,
-                                                   double j2, int &axis) {
-    bool ok = true;
-    const ArmF a = fast_forward_kinematics(j1, j2, (float)P.link_1, (float)P.link_2, ok);
-    const int v = ok ? arm_fast(G, V, a) : 2;
-    if (v != 2) return v == 1;
-    const Arm A = forward_kinematics(j1, j2, P.link_1, P.link_2);
-    int fh = 0;
-    return arm_collides<AG_ENGINE_EXACT, false>(G, V, A, P.section_eps, fh, axis);
+// ---------------------------------------------------------------- cold path: the float64 reference arithmetic
+// Kept out of line so that the hot loop's register allocation is not dictated by it.
+__device__ __noinline__ int cold_exact_decide(const ag_params &P, const GridDev &G, const GridView &V, double q1,
+                                              double q2, int c, int r) {
+    const Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
+    int fh = 0, axis = 0;
+    const bool hit = (c == 2) ? arm_collides<AG_ENGINE_EXACT, false>(G, V, A, P.section_eps, fh, axis) : (c == 1);
+    const bool reached = (r == 2) ? target_reached_cart(P, A) : (r == 1);
+    return (hit ? 1 : 0) | (reached ? 2 : 0) | (axis << 2);
+}
+
+// One step's two decisions for the FAST engine: bit0 collision, bit1 target reached, bits 2.. axis-aligned count.
+// want_reach=false (reset candidates, K2, K3): only the collision bit is meaningful.
+template <int BP>
+__device__ __forceinline__ int fast_decide(const ag_params &P, const GridDev &G, const GridView &V, const FastList *fl,
+                                           const FastConst &C, double q1, double q2, bool want_reach) {
+    bool ok;
+    const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
+    const int c = ok ? arm_fast<BP>(G, V, fl, C, a) : 2;
+    int r = 0;
+    if (want_reach) {
+        if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
+        else r = ok ? reach_fast(C, a) : 2;
+    }
+    if (c == 2 || r == 2) return cold_exact_decide(P, G, V, q1, q2, c, r);
+    return c | (r << 1);
+}
+
+// out-of-line collision_check of a candidate pose for the (rare) reset path of the rollout kernel
+template <int BP>
+__device__ __noinline__ int cold_fast_collides(const ag_params &P, const GridDev &G, const GridView &V,
+                                               const FastList *fl, double q1, double q2) {
+    const FastConst C = make_fast_const(P, G);
+    return fast_decide<BP>(P, G, V, fl, C, q1, q2, false);
 }
 
 // FAST collision_check when the float64 arm is already known (K1 needs it for its outputs)
-__device__ __forceinline__ bool fast_arm_collides(const ag_params &P, const GridDev &G, const GridView &V, const Arm &A,
-                                                  int &axis) {
+__device__ __forceinline__ bool fast_arm_collides(const ag_params &P, const GridDev &G, const GridView &V,
+                                                  const FastList *fl, const FastConst &C, const Arm &A, int &axis) {
     ArmF a;
     a.ex = (float)A.ex; a.ey = (float)A.ey; a.gx = (float)A.gx; a.gy = (float)A.gy;   // error 6e-8 < AG_DELTA_P
-    const int v = arm_fast(G, V, a);
+    const bool ok = fmax(fmax(fabs(A.ex), fabs(A.ey)), fmax(fabs(A.gx), fabs(A.gy))) < 1.0e3;
+    const int v = ok ? arm_fast<BP_ANY>(G, V, fl, C, a) : 2;
     if (v != 2) return v == 1;
     int fh = 0;
     return arm_collides<AG_ENGINE_EXACT, false>(G, V, A, P.section_eps, fh, axis);
-}
-
-// One step's two decisions (collision flag, target reached) for the rollout kernel.
-template <int ENGINE>
-__device__ __forceinline__ void step_decide(const ag_params &P, const GridDev &G, const GridView &V, double q1,
-                                            double q2, bool &hit, bool &reached, int &axis) {
-    if constexpr (ENGINE == AG_ENGINE_FAST) {
-        bool ok = true;
-        const ArmF a = fast_forward_kinematics(q1, q2, (float)P.link_1, (float)P.link_2, ok);
-        const int c = ok ? arm_fast(G, V, a) : 2;
-        int r;
-        if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
-        else r = ok ? reach_fast(P, a) : 2;
-        if (c == 2 || r == 2) {                     // undecided lane: the float64 reference arithmetic
-            const Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
-            int fh = 0;
-            hit = (c == 2) ? arm_collides<AG_ENGINE_EXACT, false>(G, V, A, P.section_eps, fh, axis) : (c == 1);
-            reached = (r == 2) ? target_reached_cart(P, A) : (r == 1);
-        } else {
-            hit = c == 1; reached = r == 1;
-        }
-    } else {
-        const Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
-        int fh = 0;
-        hit = arm_collides<ENGINE, false>(G, V, A, P.section_eps, fh, axis);
-        reached = P.choose_j_tar ? target_reached_joint(P, q1, q2) : target_reached_cart(P, A);
-    }
 }
 
 }  // namespace agd

@@ -1,6 +1,7 @@
 // ag_kernels.cu -- kernels K1..K5 of the scene_0 hot path and their extern "C" launchers.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (abstract_gym_b200/build.py).
 #include <atomic>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 
@@ -29,11 +30,40 @@ struct RolloutDev {
     unsigned long long *stats;
 };
 
-__device__ __forceinline__ GridView thread_grid_view(const GridDev &G, int64_t gid) {
+// ------------------------------------------------------------------------- per-block context
+// Every kernel that reads the grid starts the same way: stage the block's grid into shared memory
+// (or point at global memory), and for the FAST engine build the obstacle list of small sparse grids.
+struct BlockCtx {
     GridView V;
-    V.bits = G.bits + grid_of_env(G, gid) * G.stride_words;
-    V.min_x = G.min_x; V.min_y = G.min_y;
-    return V;
+    const FastList *fl;   // nullptr: not applicable (grid not staged / engine != FAST)
+};
+
+template <int ENGINE>
+__device__ __forceinline__ BlockCtx block_prologue(const GridDev &G, int64_t env_id0, int64_t n, unsigned char *smem,
+                                                   FastList *s_fl) {
+    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
+    BlockCtx B;
+    B.fl = nullptr;
+    if (G.stage) {
+        B.V = stage_grid(G, env_id0 + e0, smem);
+        if (ENGINE == AG_ENGINE_FAST) {
+            build_fast_list(G, B.V, s_fl);
+            B.fl = s_fl;
+        }
+    } else {
+        B.V.bits = G.bits + grid_of_env(G, env_id0 + min(e, n - 1)) * G.stride_words;
+        B.V.min_x = G.min_x; B.V.min_y = G.min_y;
+    }
+    return B;
+}
+
+// block statistics: shared-memory atomics at (rare) events, one global atomic per slot per block
+__device__ __forceinline__ void stats_flush(unsigned long long *s_acc, unsigned long long *gstats) {
+    __syncthreads();
+    if (threadIdx.x < AG_ST_COUNT && gstats != nullptr) {
+        const unsigned long long v = s_acc[threadIdx.x];
+        if (v != 0) atomicAdd(&gstats[threadIdx.x], v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------- K5
@@ -83,23 +113,19 @@ __global__ void k_forward_kinematics(ag_params P, const double *__restrict__ j1,
     reinterpret_cast<double4 *>(out)[i] = make_double4(A.ex, A.ey, A.gx, A.gy);
 }
 
-// engine dispatch shared by K1..K3: FAST decides with the float32 filter and re-evaluates the
-// undecided lanes with the EXACT engine (ag_fast.cuh), so all engines return the same flag.
-// NEED_ARM: the caller wants the float64 arm A (K1's ee/dist outputs and reach test).
-template <int ENGINE, bool WANT_FIRST, bool NEED_ARM>
-__device__ __forceinline__ bool pose_collides(const ag_params &P, const GridDev &G, const GridView &V, double j1,
-                                              double j2, Arm &A, int &fh, int &axis) {
+// collision_check of one pose for K2/K3 (flag only unless WANT_FIRST)
+template <int ENGINE, bool WANT_FIRST, int BP = BP_ANY, bool COLD = false>
+__device__ __forceinline__ bool pose_collides(const ag_params &P, const GridDev &G, const BlockCtx &B,
+                                              const FastConst &C, double j1, double j2, int &fh, int &axis) {
     if constexpr (ENGINE == AG_ENGINE_FAST && !WANT_FIRST) {
-        if constexpr (NEED_ARM) {
-            A = forward_kinematics(j1, j2, P.link_1, P.link_2);
-            return fast_arm_collides(P, G, V, A, axis);
-        } else {
-            return fast_pose_collides(P, G, V, j1, j2, axis);
-        }
+        const int d = COLD ? cold_fast_collides<BP>(P, G, B.V, B.fl, j1, j2)
+                           : fast_decide<BP>(P, G, B.V, B.fl, C, j1, j2, false);
+        axis += d >> 2;
+        return d & 1;
     } else {
-        A = forward_kinematics(j1, j2, P.link_1, P.link_2);
+        const Arm A = forward_kinematics(j1, j2, P.link_1, P.link_2);
         return arm_collides<ENGINE == AG_ENGINE_BRUTE ? AG_ENGINE_BRUTE : AG_ENGINE_EXACT, WANT_FIRST>(
-            G, V, A, P.section_eps, fh, axis);
+            G, B.V, A, P.section_eps, fh, axis);
     }
 }
 
@@ -110,20 +136,19 @@ __global__ void __launch_bounds__(AG_BLOCK) k_collision(const ag_params P, const
                                                         uint8_t *__restrict__ hit, int32_t *__restrict__ first_hit,
                                                         int64_t n, int64_t env_id0) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
-    GridView V;
-    if (G.stage) V = stage_grid(G, env_id0 + e0, smem);
-    else V = thread_grid_view(G, env_id0 + min(e, n - 1));
+    __shared__ FastList s_fl;
+    const BlockCtx B = block_prologue<ENGINE>(G, env_id0, n, smem, &s_fl);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    Arm A;
+    const FastConst C = make_fast_const(P, G);
     int fh = INT_MAX, axis = 0;
-    const bool h = pose_collides<ENGINE, WANT_FIRST, false>(P, G, V, j1[e], j2[e], A, fh, axis);
+    const bool h = pose_collides<ENGINE, WANT_FIRST>(P, G, B, C, j1[e], j2[e], fh, axis);
     hit[e] = h ? 1 : 0;
     if (WANT_FIRST) first_hit[e] = h ? fh : -1;
 }
 
 // ------------------------------------------------------------------------------------------- K1
-// scenario/scene_0.py:88-103
+// scenario/scene_0.py:88-103.  The float64 arm is always computed here (ee / dist outputs).
 template <int ENGINE, bool ACT_F32, bool WANT_FIRST>
 __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const GridDev G, double *__restrict__ j1,
                                                    double *__restrict__ j2, const void *__restrict__ actions,
@@ -132,14 +157,12 @@ __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const Grid
                                                    int32_t *__restrict__ first_hit, unsigned long long *stats,
                                                    int64_t n, int64_t env_id0) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ FastList s_fl;
     __shared__ unsigned long long s_acc[AG_ST_COUNT];
     if (threadIdx.x < AG_ST_COUNT) s_acc[threadIdx.x] = 0;
-    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
-    GridView V;
-    if (G.stage) V = stage_grid(G, env_id0 + e0, smem);
-    else V = thread_grid_view(G, env_id0 + min(e, n - 1));
+    const BlockCtx B = block_prologue<ENGINE>(G, env_id0, n, smem, &s_fl);
     __syncthreads();
-    long long st[AG_ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) {
         double d1, d2;
         if (ACT_F32) {
@@ -152,9 +175,16 @@ __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const Grid
         const double q1 = __dadd_rn(j1[e], d1), q2 = __dadd_rn(j2[e], d2);   // two_joint_robot.py:71-72
         float rw = reward[e];
         uint8_t fl = flags[e];
-        Arm A;
+        const Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
         int fh = INT_MAX, axis = 0;
-        const bool h = pose_collides<ENGINE, WANT_FIRST, true>(P, G, V, q1, q2, A, fh, axis);
+        bool h;
+        if constexpr (ENGINE == AG_ENGINE_FAST && !WANT_FIRST) {
+            const FastConst C = make_fast_const(P, G);
+            h = fast_arm_collides(P, G, B.V, B.fl, C, A, axis);
+        } else {
+            h = arm_collides<ENGINE == AG_ENGINE_BRUTE ? AG_ENGINE_BRUTE : AG_ENGINE_EXACT, WANT_FIRST>(
+                G, B.V, A, P.section_eps, fh, axis);
+        }
         if (h) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }       // scene_0.py:95-97
         if (target_reached(P, q1, q2, A)) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }   // :98-100
         j1[e] = q1; j2[e] = q2; reward[e] = rw; flags[e] = fl;
@@ -163,21 +193,25 @@ __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const Grid
             reinterpret_cast<double2 *>(dist)[e] =
                 make_double2(fabs(__dsub_rn(P.target_x, A.gx)), fabs(__dsub_rn(P.target_y, A.gy)));
         if (WANT_FIRST) first_hit[e] = h ? fh : -1;
-        st[AG_ST_ENV_STEPS] = 1;
-        st[AG_ST_AXIS_ALIGNED] = axis;
+        atomicAdd(&s_acc[AG_ST_ENV_STEPS], 1ull);
+        if (axis) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)axis);
     }
-    if (stats) block_accumulate_stats(st, stats, s_acc);
+    stats_flush(s_acc, stats);
 }
 
 // shared by K3 and K4: scenario/scene_0.py:174-181 with a bound.  `colliding` is the
 // collision_check() of the current pose.
-template <int ENGINE, bool HAS_RESET_U>
-__device__ __forceinline__ void resample_pose(const ag_params &P, const GridDev &G, const GridView &V, bool colliding,
-                                              double &j1, double &j2, uint32_t &rc, const double *reset_u_env,
-                                              int32_t R, uint64_t seed, uint64_t gid, long long (&st)[AG_ST_COUNT]) {
+template <int ENGINE, bool HAS_RESET_U, int BP = BP_ANY, bool COLD = false>
+__device__ __forceinline__ void resample_pose(const ag_params &P, const GridDev &G, const BlockCtx &B,
+                                              const FastConst &C, bool colliding, double &j1, double &j2,
+                                              uint32_t &rc, const double *reset_u_env, int32_t R, uint64_t seed,
+                                              uint64_t gid, unsigned long long *s_acc) {
     int tries = 0;
     while (colliding) {
-        if (tries >= P.max_reset_tries || (HAS_RESET_U && rc >= (uint32_t)R)) { ++st[AG_ST_STUCK_RESETS]; break; }
+        if (tries >= P.max_reset_tries || (HAS_RESET_U && rc >= (uint32_t)R)) {
+            atomicAdd(&s_acc[AG_ST_STUCK_RESETS], 1ull);
+            break;
+        }
         double u0, u1;
         if (HAS_RESET_U) {
             const double2 u = reinterpret_cast<const double2 *>(reset_u_env)[rc];
@@ -188,10 +222,9 @@ __device__ __forceinline__ void resample_pose(const ag_params &P, const GridDev 
         ++rc; ++tries;
         j1 = __dmul_rn(__dmul_rn(u0, 3.141592653589793), 2.0);    // scene_0.py:180  rand()*pi*2.0
         j2 = __dmul_rn(__dmul_rn(u1, 3.141592653589793), 2.0);    // :181
-        Arm B;
         int fh = 0, axis = 0;
-        colliding = pose_collides<ENGINE, false, false>(P, G, V, j1, j2, B, fh, axis);
-        st[AG_ST_AXIS_ALIGNED] += axis;
+        colliding = pose_collides<ENGINE, false, BP, COLD>(P, G, B, C, j1, j2, fh, axis);
+        if (axis) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)axis);
     }
 }
 
@@ -205,44 +238,55 @@ __global__ void __launch_bounds__(AG_BLOCK) k_reset(const ag_params P, const Gri
                                                     int32_t R, uint64_t seed, int clear_flags, unsigned long long *stats,
                                                     int64_t n, int64_t env_id0) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ FastList s_fl;
     __shared__ unsigned long long s_acc[AG_ST_COUNT];
     if (threadIdx.x < AG_ST_COUNT) s_acc[threadIdx.x] = 0;
-    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
-    GridView V;
-    if (G.stage) V = stage_grid(G, env_id0 + e0, smem);
-    else V = thread_grid_view(G, env_id0 + min(e, n - 1));
+    const BlockCtx B = block_prologue<ENGINE>(G, env_id0, n, smem, &s_fl);
     __syncthreads();
-    long long st[AG_ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n && (mask == nullptr || mask[e] != 0)) {
+        const FastConst C = make_fast_const(P, G);
         double q1 = j1[e], q2 = j2[e];
         uint32_t rc = reset_ctr[e];
-        Arm A;
         int fh = 0, axis = 0;
-        const bool h = pose_collides<ENGINE, false, false>(P, G, V, q1, q2, A, fh, axis);
-        st[AG_ST_AXIS_ALIGNED] += axis;
-        resample_pose<ENGINE, HAS_RESET_U>(P, G, V, h, q1, q2, rc, HAS_RESET_U ? reset_u + (int64_t)e * R * 2 : nullptr,
-                                           R, seed, (uint64_t)(env_id0 + e), st);
+        const bool h = pose_collides<ENGINE, false>(P, G, B, C, q1, q2, fh, axis);
+        if (axis) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)axis);
+        resample_pose<ENGINE, HAS_RESET_U>(P, G, B, C, h, q1, q2, rc, HAS_RESET_U ? reset_u + (int64_t)e * R * 2 : nullptr,
+                                           R, seed, (uint64_t)(env_id0 + e), s_acc);
         j1[e] = q1; j2[e] = q2; reset_ctr[e] = rc;
         if (clear_flags) { reward[e] = 0.0f; flags[e] = 0; }       // scene_0.py:111-113
     }
-    if (stats) block_accumulate_stats(st, stats, s_acc);
+    stats_flush(s_acc, stats);
 }
 
 // ------------------------------------------------------------------------------------------- K4
 // experiment/experiment_0.py:20-34 fused over K steps; env state lives in registers for the
 // whole launch, the only per-step HBM traffic is the action read and the record write.
-template <int ENGINE, bool HAS_ACT, bool HAS_RESET_U, bool RECORD>
-__global__ void __launch_bounds__(AG_BLOCK) k_rollout(const ag_params P, const GridDev G, const RolloutDev A) {
+template <int ENGINE, int BP>
+__device__ __forceinline__ int step_decide(const ag_params &P, const GridDev &G, const BlockCtx &B,
+                                           const FastConst &C, double q1, double q2) {
+    if constexpr (ENGINE == AG_ENGINE_FAST) {
+        return fast_decide<BP>(P, G, B.V, B.fl, C, q1, q2, true);
+    } else {
+        const Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
+        int fh = 0, axis = 0;
+        const bool h = arm_collides<ENGINE, false>(G, B.V, A, P.section_eps, fh, axis);
+        return (h ? 1 : 0) | (target_reached(P, q1, q2, A) ? 2 : 0) | (axis << 2);
+    }
+}
+
+template <int ENGINE, int BP, bool HAS_ACT, bool HAS_RESET_U, bool RECORD>
+__global__ void __launch_bounds__(AG_BLOCK, ENGINE == AG_ENGINE_FAST ? (BP == BP_LIST ? 4 : 2) : 1)
+k_rollout(const ag_params P, const GridDev G, const RolloutDev A) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ FastList s_fl;
     __shared__ unsigned long long s_acc[AG_ST_COUNT];
     if (threadIdx.x < AG_ST_COUNT) s_acc[threadIdx.x] = 0;
-    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
-    GridView V;
-    if (G.stage) V = stage_grid(G, A.env_id0 + e0, smem);
-    else V = thread_grid_view(G, A.env_id0 + min(e, A.n - 1));
+    const BlockCtx B = block_prologue<ENGINE>(G, A.env_id0, A.n, smem, &s_fl);
     __syncthreads();
-    long long st[AG_ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < A.n) {
+        const FastConst C = make_fast_const(P, G);
         const uint64_t gid = (uint64_t)(A.env_id0 + e);
         double q1 = A.j1[e], q2 = A.j2[e];
         float rw = A.reward[e];
@@ -250,10 +294,13 @@ __global__ void __launch_bounds__(AG_BLOCK) k_rollout(const ag_params P, const G
         uint32_t sc = A.step_ctr[e], rc = A.reset_ctr[e], el = A.ep_len[e];
         const float2 *act = HAS_ACT ? reinterpret_cast<const float2 *>(A.actions) + e : nullptr;
         const double *ru = HAS_RESET_U ? A.reset_u + (int64_t)e * A.R * 2 : nullptr;
-        for (int t = 0; t < A.K; ++t) {
+        const float rw_coll = (float)P.reward_collision, rw_reach = (float)P.reward_reach;
+        int64_t o = e;
+        for (int t = 0; t < A.K; ++t, o += A.row_stride) {
             double d1, d2;
             if (HAS_ACT) {
-                const float2 a = __ldcs(act + (int64_t)t * A.row_stride);   // streamed once
+                const float2 a = __ldcs(act);                                // streamed once
+                act += A.row_stride;
                 d1 = (double)a.x; d2 = (double)a.y;
             } else {
                 double u0, u1;
@@ -263,37 +310,36 @@ __global__ void __launch_bounds__(AG_BLOCK) k_rollout(const ag_params P, const G
             }
             ++sc;
             q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);                  // two_joint_robot.py:71-72
-            bool h, reached;
-            int axis = 0;
-            step_decide<ENGINE>(P, G, V, q1, q2, h, reached, axis);
-            st[AG_ST_AXIS_ALIGNED] += axis;
-            if (h) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }            // scene_0.py:95-97
-            if (reached) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }               // :98-100
+            const int d = step_decide<ENGINE, BP>(P, G, B, C, q1, q2);
+            if (d & 1) { rw = rw_coll; fl |= AG_FLAG_COLLISION; }            // scene_0.py:95-97
+            if (d & 2) { rw = rw_reach; fl |= AG_FLAG_DONE; }                // :98-100
             if (RECORD) {                                                    // experiment_0.py:23-25
-                const int64_t o = (int64_t)t * A.row_stride + e;
                 __stcs(A.rec_j1 + o, (float)q1);
                 __stcs(A.rec_j2 + o, (float)q2);
                 __stcs(A.rec_reward + o, rw);
                 A.rec_flags[o] = (uint8_t)fl;
             }
             ++el;
-            if (fl) {                                                        // experiment_0.py:30-34
-                ++st[AG_ST_EPISODES];
-                st[AG_ST_COLLISIONS] += (fl & AG_FLAG_COLLISION) ? 1 : 0;
-                st[AG_ST_SUCCESSES] += (fl & AG_FLAG_DONE) ? 1 : 0;
-                st[AG_ST_EP_LEN_SUM] += el;
-                st[AG_ST_RETURN_MILLI] += llrintf(rw * 1e-3f);
-                el = 0;
-                // Scene.reset(): the pose is unchanged since the step, so collision_check() == h
-                resample_pose<ENGINE, HAS_RESET_U>(P, G, V, h, q1, q2, rc, ru, A.R, A.seed, gid, st);
-                rw = 0.0f; fl = 0;                                           // scene_0.py:111-113
+            if (fl | (d >> 2)) {                                             // experiment_0.py:30-34 (rare)
+                if (d >> 2) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)(d >> 2));
+                if (fl) {
+                    atomicAdd(&s_acc[AG_ST_EPISODES], 1ull);
+                    if (fl & AG_FLAG_COLLISION) atomicAdd(&s_acc[AG_ST_COLLISIONS], 1ull);
+                    if (fl & AG_FLAG_DONE) atomicAdd(&s_acc[AG_ST_SUCCESSES], 1ull);
+                    atomicAdd(&s_acc[AG_ST_EP_LEN_SUM], (unsigned long long)el);
+                    atomicAdd(&s_acc[AG_ST_RETURN_MILLI], (unsigned long long)(long long)llrintf(rw * 1e-3f));
+                    el = 0;
+                    // Scene.reset(): the pose is unchanged since the step, so collision_check() == (d & 1)
+                    resample_pose<ENGINE, HAS_RESET_U, BP, true>(P, G, B, C, (d & 1) != 0, q1, q2, rc, ru, A.R, A.seed, gid, s_acc);
+                    rw = 0.0f; fl = 0;                                       // scene_0.py:111-113
+                }
             }
         }
-        st[AG_ST_ENV_STEPS] = A.K;
+        atomicAdd(&s_acc[AG_ST_ENV_STEPS], (unsigned long long)A.K);
         A.j1[e] = q1; A.j2[e] = q2; A.reward[e] = rw; A.flags[e] = (uint8_t)fl;
         A.step_ctr[e] = sc; A.reset_ctr[e] = rc; A.ep_len[e] = el;
     }
-    block_accumulate_stats(st, A.stats, s_acc);
+    stats_flush(s_acc, A.stats);
 }
 
 // ------------------------------------------------------------------------------------- host side
@@ -305,11 +351,16 @@ int stage_max_bytes() {
     return v;
 }
 
-ag_status make_grid_dev(const ag_grid *g, int64_t env_id0, GridDev *out, size_t *smem_bytes) {
+ag_status make_grid_dev(const ag_params *p, const ag_grid *g, int64_t env_id0, int engine, GridDev *out,
+                        size_t *smem_bytes) {
     if (!g || !g->bits || !g->min_x || !g->min_y) return AG_ERR_NULL;
     if (g->S < 2 || g->words_per_row != (g->S + 31) / 32 || g->n_grids < 1 || g->envs_per_grid < 1 ||
         g->grid_stride_words < (int64_t)g->S * g->words_per_row)
         return AG_ERR_SHAPE;
+    // the FAST engine's error budget (ag_fast.cuh) assumes scene_0-class magnitudes
+    if (engine == AG_ENGINE_FAST && p &&
+        !(p->link_1 > 0 && p->link_2 > 0 && p->link_1 <= 1.0 && p->link_2 <= 1.0 && g->env_size <= 4.0))
+        return AG_ERR_MODE;
     GridDev d;
     d.bits = g->bits; d.min_x = g->min_x; d.min_y = g->min_y;
     d.side = g->side; d.half = g->env_size / 2.0; d.inv_side = 1.0 / g->side;
@@ -350,19 +401,19 @@ inline unsigned blocks_for(int64_t n) { return (unsigned)((n + AG_BLOCK - 1) / A
         default: return AG_ERR_MODE;                                      \
     }
 
-template <int E, bool HA, bool HR, bool REC>
+template <int E, int BP, bool HA, bool HR, bool REC>
 ag_status launch_rollout_t(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s) {
-    auto k = k_rollout<E, HA, HR, REC>;
+    auto k = k_rollout<E, BP, HA, HR, REC>;
     ag_status st = set_smem(k, smem);
     if (st) return st;
     k<<<blocks_for(A.n), AG_BLOCK, smem, s>>>(P, G, A);
     return launched();
 }
 
-template <int E>
+template <int E, int BP>
 ag_status launch_rollout_e(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s) {
     const bool ha = A.actions != nullptr, hr = A.reset_u != nullptr, rec = A.rec_j1 != nullptr;
-#define AG_RO(HA, HR, REC) return launch_rollout_t<E, HA, HR, REC>(P, G, A, smem, s)
+#define AG_RO(HA, HR, REC) return launch_rollout_t<E, BP, HA, HR, REC>(P, G, A, smem, s)
     if (ha) { if (hr) { if (rec) AG_RO(true, true, true); else AG_RO(true, true, false); }
               else    { if (rec) AG_RO(true, false, true); else AG_RO(true, false, false); } }
     else    { if (hr) { if (rec) AG_RO(false, true, true); else AG_RO(false, true, false); }
@@ -372,7 +423,7 @@ ag_status launch_rollout_e(const ag_params &P, const GridDev &G, const RolloutDe
 
 }  // namespace
 
-// internal (used by ag_host.cu): rollout with explicit grid descriptor validation done
+// internal (also used by ag_host.cu): rollout with explicit action/record row stride
 ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, int64_t row_stride,
                           void *stream) {
     if (!p || !g || !a) return AG_ERR_NULL;
@@ -387,7 +438,7 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
     if (row_stride < a->n) return AG_ERR_SHAPE;
     GridDev G;
     size_t smem;
-    ag_status st = make_grid_dev(g, a->env_id0, &G, &smem);
+    ag_status st = make_grid_dev(p, g, a->env_id0, a->engine, &G, &smem);
     if (st) return st;
     RolloutDev A;
     A.n = a->n; A.env_id0 = a->env_id0; A.row_stride = row_stride; A.K = a->K; A.R = a->R; A.seed = a->seed;
@@ -397,8 +448,16 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
     A.rec_j1 = a->rec_j1; A.rec_j2 = a->rec_j2; A.rec_reward = a->rec_reward; A.rec_flags = a->rec_flags;
     A.stats = reinterpret_cast<unsigned long long *>(a->stats);
     cudaStream_t s = (cudaStream_t)stream;
-    AG_DISPATCH_ENGINE(a->engine, return launch_rollout_e<E>(*p, G, A, smem, s));
-    return AG_OK;
+    // FAST engine: the obstacle-list broad phase when the caller vouches for small sparse staged grids
+    // (ag_grid.max_occupied); a block whose grid turns out not to qualify falls back to EXACT per lane.
+    if (a->engine == AG_ENGINE_FAST) {
+        const bool list = G.stage && g->S <= 32 && g->max_occupied >= 0 && g->max_occupied <= AG_LIST_MAX;
+        if (list) return launch_rollout_e<AG_ENGINE_FAST, BP_LIST>(*p, G, A, smem, s);
+        return launch_rollout_e<AG_ENGINE_FAST, BP_TRAVERSAL>(*p, G, A, smem, s);
+    }
+    if (a->engine == AG_ENGINE_EXACT) return launch_rollout_e<AG_ENGINE_EXACT, BP_ANY>(*p, G, A, smem, s);
+    if (a->engine == AG_ENGINE_BRUTE) return launch_rollout_e<AG_ENGINE_BRUTE, BP_ANY>(*p, G, A, smem, s);
+    return AG_ERR_MODE;
 }
 
 extern "C" {
@@ -442,7 +501,7 @@ ag_status ag_collision_check(const ag_params *p, const ag_grid *g, const double 
     if (!p || !g) return AG_ERR_NULL;
     GridDev G;
     size_t smem;
-    ag_status st = make_grid_dev(g, env_id0, &G, &smem);
+    ag_status st = make_grid_dev(p, g, env_id0, engine, &G, &smem);
     if (st) return st;
     if (n == 0) return AG_OK;
     if (!j1 || !j2 || !hit) return AG_ERR_NULL;
@@ -468,7 +527,7 @@ ag_status ag_step(const ag_params *p, const ag_grid *g, double *j1, double *j2, 
     if (!p || !g) return AG_ERR_NULL;
     GridDev G;
     size_t smem;
-    ag_status st = make_grid_dev(g, env_id0, &G, &smem);
+    ag_status st = make_grid_dev(p, g, env_id0, engine, &G, &smem);
     if (st) return st;
     if (n == 0) return AG_OK;
     if (!j1 || !j2 || !actions || !reward || !flags) return AG_ERR_NULL;
@@ -492,7 +551,7 @@ ag_status ag_reset(const ag_params *p, const ag_grid *g, double *j1, double *j2,
     if (!p || !g) return AG_ERR_NULL;
     GridDev G;
     size_t smem;
-    ag_status st = make_grid_dev(g, env_id0, &G, &smem);
+    ag_status st = make_grid_dev(p, g, env_id0, engine, &G, &smem);
     if (st) return st;
     if (n == 0) return AG_OK;
     if (!j1 || !j2 || !reset_ctr || (clear_flags && (!reward || !flags))) return AG_ERR_NULL;

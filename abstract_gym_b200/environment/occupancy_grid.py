@@ -19,7 +19,7 @@ from ..utils.geometry import Point, Square
 class DeviceGrid:
     """What the kernels read: bits[n_grids][stride_words] uint32, min_x[S], min_y[S] float64."""
 
-    def __init__(self, bits, S, environment_size, n_grids=1, envs_per_grid=1 << 62, device=None):
+    def __init__(self, bits, S, environment_size, n_grids=1, envs_per_grid=1 << 62, max_occupied=None):
         lib = _lib.load()
         self.device = bits.device
         self.S = int(S)
@@ -30,6 +30,7 @@ class DeviceGrid:
         self.envs_per_grid = int(envs_per_grid)
         assert bits.dtype == torch.int32 and bits.numel() == self.n_grids * self.stride_words
         self.bits = bits
+        self.max_occupied = -1 if max_occupied is None else int(max_occupied)
         spad = (self.S + 1) & ~1
         mx = np.zeros(spad, dtype=np.float64)
         my = np.zeros(spad, dtype=np.float64)
@@ -46,6 +47,7 @@ class DeviceGrid:
         g.bits, g.min_x, g.min_y = self.bits.data_ptr(), self.min_x.data_ptr(), self.min_y.data_ptr()
         g.side, g.env_size = self.side, self.environment_size
         g.S, g.words_per_row, g.n_grids = self.S, self.words_per_row, self.n_grids
+        g.max_occupied = self.max_occupied
         g.grid_stride_words = self.stride_words
         g.envs_per_grid = self.envs_per_grid if envs_per_grid is None else int(envs_per_grid)
         return g
@@ -61,7 +63,7 @@ class DeviceGrid:
         _lib.check(lib.ag_grid_pack_host(occ8.ctypes.data_as(C.c_void_p), occ8.shape[0], occ8.shape[1],
                                          words.ctypes.data_as(C.c_void_p)), "ag_grid_pack_host")
         bits = torch.from_numpy(words.view(np.int32)).to(dev)
-        return cls(bits, occ8.shape[0], environment_size)
+        return cls(bits, occ8.shape[0], environment_size, max_occupied=int(occ8.sum()))
 
     @classmethod
     def from_device_matrices(cls, occ, environment_size=1.6, envs_per_grid=1 << 62):
@@ -77,7 +79,8 @@ class DeviceGrid:
         stride = int(lib.ag_grid_stride_words(S))
         bits = torch.zeros(G * stride, dtype=torch.int32, device=dev)
         _lib.check(lib.ag_grid_pack(ptr(occ8), S, G, ptr(bits), stride, stream_ptr(dev)), "ag_grid_pack")
-        return cls(bits, S, environment_size, n_grids=G, envs_per_grid=envs_per_grid)
+        return cls(bits, S, environment_size, n_grids=G, envs_per_grid=envs_per_grid,
+                   max_occupied=int(occ8.sum(dim=(1, 2), dtype=torch.int64).max().item()))
 
     def unpack(self):
         """[G,S,S] uint8 numpy (inverse of the packing; for tests and tools)"""

@@ -76,7 +76,7 @@ typedef struct ag_grid {
     int32_t S;
     int32_t words_per_row;           /* ceil(S/32) */
     int32_t n_grids;
-    int32_t reserved;
+    int32_t max_occupied;            /* upper bound on occupied cells of any grid; < 0 = unknown (hint only) */
     int64_t grid_stride_words;       /* >= S*words_per_row, multiple of 4 (16-byte rows for bulk copies) */
     int64_t envs_per_grid;
 } ag_grid;
