@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(HERE, "..", "include")
-LIB = os.path.join(HERE, "libabstract_gym_b200.so")
+LIB = os.environ.get("AG_LIB_PATH") or os.path.join(HERE, "libabstract_gym_b200.so")   # AG_LIB_PATH: A/B builds
 SOURCES = ["ag_kernels.cu", "ag_host.cu"]
 HEADERS = ["ag_device.cuh", "ag_fast.cuh", os.path.join(INCLUDE, "abstract_gym_b200.h")]
 
@@ -32,6 +32,8 @@ def find_nvcc() -> str:
 
 
 def needs_build() -> bool:
+    if os.environ.get("AG_LIB_PATH"):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)

@@ -23,6 +23,13 @@
 #pragma once
 #include "ag_device.cuh"
 
+// cold paths: out of line (ABI call) or inlined; see DESIGN.md "register allocation of K4"
+#ifdef AG_COLD_INLINE
+#define AG_COLD __device__ __forceinline__
+#else
+#define AG_COLD __device__ __noinline__
+#endif
+
 namespace agd {
 
 constexpr float AG_DELTA_P = 3.0e-7f;
@@ -38,7 +45,7 @@ struct ArmF { float ex, ey, gx, gy; };
 struct FastConst {
     float l1, l2, side, half, inv_side, tx, ty, reach_eps;
 };
-__device__ __forceinline__ FastConst make_fast_const(const ag_params &P, const GridDev &G) {
+__host__ __device__ __forceinline__ FastConst make_fast_const(const ag_params &P, const GridDev &G) {
     FastConst C;
     C.l1 = (float)P.link_1; C.l2 = (float)P.link_2;
     C.side = (float)G.side; C.half = (float)G.half; C.inv_side = (float)G.inv_side;
@@ -170,24 +177,27 @@ __device__ __forceinline__ int arm_fast_list(const FastList *fl, const ArmF &a, 
     const float x1lo = fminf(0.0f, a.ex), x1hi = fmaxf(0.0f, a.ex), y1lo = fminf(0.0f, a.ey), y1hi = fmaxf(0.0f, a.ey);
     const float x2lo = fminf(a.ex, a.gx), x2hi = fmaxf(a.ex, a.gx), y2lo = fminf(a.ey, a.gy), y2hi = fmaxf(a.ey, a.gy);
     uint32_t cand = 0;
+#pragma unroll 1
     for (int k = 0; k < m; ++k) {
         const float4 q = fl->sq[k];
         const bool o1 = (x1hi - q.x > -AG_M) && (q.z - x1lo > -AG_M) && (y1hi - q.y > -AG_M) && (q.w - y1lo > -AG_M);
         const bool o2 = (x2hi - q.x > -AG_M) && (q.z - x2lo > -AG_M) && (y2hi - q.y > -AG_M) && (q.w - y2lo > -AG_M);
-        cand |= (o1 ? 1u : 0u) << (2 * k) | (o2 ? 2u : 0u) << (2 * k);
+        cand |= ((o1 ? 1u : 0u) | (o2 ? 2u : 0u)) << (2 * k);
     }
+    // narrow phase on the surviving (link, cell) pairs; the link is rebuilt per pair from `a`
+    // (a dozen instructions) instead of keeping two LinkF live: registers matter more here
     int result = 0;
-    if (cand) {
-        const LinkF L1 = make_link_f(0.0f, 0.0f, a.ex, a.ey, C.side);
-        const LinkF L2 = make_link_f(a.ex, a.ey, a.gx, a.gy, C.side);
-        while (cand) {
-            const int b = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const float4 q = fl->sq[b >> 1];
-            const int v = narrow_f32((b & 1) ? L2 : L1, q.x, q.y, q.z, q.w);
-            if (v == 1) return 1;
-            result |= v;
-        }
+#pragma unroll 1
+    while (cand) {
+        const int b = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const float4 q = fl->sq[b >> 1];
+        const bool second = (b & 1) != 0;
+        const LinkF L = make_link_f(second ? a.ex : 0.0f, second ? a.ey : 0.0f, second ? a.gx : a.ex,
+                                    second ? a.gy : a.ey, C.side);
+        const int v = narrow_f32(L, q.x, q.y, q.z, q.w);
+        if (v == 1) return 1;
+        result |= v;
     }
     return result;
 }
@@ -276,13 +286,27 @@ __device__ __forceinline__ int reach_fast(const FastConst &C, const ArmF &a) {
 
 // ---------------------------------------------------------------- cold path: the float64 reference arithmetic
 // Kept out of line so that the hot loop's register allocation is not dictated by it.
-__device__ __noinline__ int cold_exact_decide(const ag_params &P, const GridDev &G, const GridView &V, double q1,
+AG_COLD int cold_exact_decide(const ag_params &P, const GridDev &G, const GridView &V, double q1,
                                               double q2, int c, int r) {
     const Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
     int fh = 0, axis = 0;
     const bool hit = (c == 2) ? arm_collides<AG_ENGINE_EXACT, false>(G, V, A, P.section_eps, fh, axis) : (c == 1);
     const bool reached = (r == 2) ? target_reached_cart(P, A) : (r == 1);
     return (hit ? 1 : 0) | (reached ? 2 : 0) | (axis << 2);
+}
+
+// The call-free float32 filter of one step: returns c | (r << 2) with c (collision) and r (target
+// reached) each 0 = certainly not, 1 = certainly, 2 = undecided (needs cold_exact_decide).
+template <int BP>
+__device__ __forceinline__ int fast_filter(const ag_params &P, const GridDev &G, const GridView &V, const FastList *fl,
+                                           const FastConst &C, double q1, double q2) {
+    bool ok;
+    const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
+    const int c = ok ? arm_fast<BP>(G, V, fl, C, a) : 2;
+    int r;
+    if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
+    else r = ok ? reach_fast(C, a) : 2;
+    return c | (r << 2);
 }
 
 // One step's two decisions for the FAST engine: bit0 collision, bit1 target reached, bits 2.. axis-aligned count.
@@ -304,7 +328,7 @@ __device__ __forceinline__ int fast_decide(const ag_params &P, const GridDev &G,
 
 // out-of-line collision_check of a candidate pose for the (rare) reset path of the rollout kernel
 template <int BP>
-__device__ __noinline__ int cold_fast_collides(const ag_params &P, const GridDev &G, const GridView &V,
+AG_COLD int cold_fast_collides(const ag_params &P, const GridDev &G, const GridView &V,
                                                const FastList *fl, double q1, double q2) {
     const FastConst C = make_fast_const(P, G);
     return fast_decide<BP>(P, G, V, fl, C, q1, q2, false);

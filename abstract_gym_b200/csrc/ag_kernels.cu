@@ -13,6 +13,9 @@ using namespace agd;
 namespace {
 
 constexpr int AG_BLOCK = 256;
+#ifndef AG_FAST_BLOCKS_PER_SM
+#define AG_FAST_BLOCKS_PER_SM 4
+#endif
 std::atomic<long long> g_launches{0};
 
 struct RolloutDev {
@@ -262,6 +265,10 @@ __global__ void __launch_bounds__(AG_BLOCK) k_reset(const ag_params P, const Gri
 // ------------------------------------------------------------------------------------------- K4
 // experiment/experiment_0.py:20-34 fused over K steps; env state lives in registers for the
 // whole launch, the only per-step HBM traffic is the action read and the record write.
+//
+// Register discipline: the hot loop keeps (q1, q2, reward, flags, ep_len, prefetched action) live;
+// everything an episode end needs (reset counter, Philox key, candidate list) is re-derived
+// inside the out-of-line cold_terminal(), so the loop fits the register budget without spills.
 template <int ENGINE, int BP>
 __device__ __forceinline__ int step_decide(const ag_params &P, const GridDev &G, const BlockCtx &B,
                                            const FastConst &C, double q1, double q2) {
@@ -275,69 +282,158 @@ __device__ __forceinline__ int step_decide(const ag_params &P, const GridDev &G,
     }
 }
 
+// Everything thread-private that the hot loop carries.  It lives in registers inside the inner
+// loop and is spilled to this struct (local memory) only around the out-of-line cold section, so
+// that no value is live across the ABI call: that is what keeps the inner loop spill-free under a
+// 64-register budget (DESIGN.md "register allocation of K4").
+struct HotCtx {
+    double q1, q2;
+    const float2 *act;       // action of step t+1 (prefetched into a_next)
+    const uint32_t *vbits;   // this thread's grid view
+    const double *vminx, *vminy;
+    const FastList *fl;
+    int64_t o;               // record offset of step t
+    int64_t e;               // env index within the launch
+    float2 a_next;
+    float rw;
+    uint32_t flags, el, mask;
+    int t, d, undecided;
+};
+
+// Cold section, out of line: (1) finish a step whose float32 filter was undecided with the
+// float64 reference arithmetic, (2) episode end (experiment_0.py:30-34): statistics + Scene.reset().
+template <int ENGINE, int BP, bool HAS_RESET_U, bool RECORD>
+__device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, const RolloutDev &A, HotCtx *hc,
+                                          unsigned long long *s_acc) {
+    double q1 = hc->q1, q2 = hc->q2;
+    float rw = hc->rw;
+    uint32_t fl = hc->flags, el = hc->el;
+    int d = hc->d;
+    BlockCtx B;
+    B.V.bits = hc->vbits; B.V.min_x = hc->vminx; B.V.min_y = hc->vminy; B.fl = hc->fl;
+    if (hc->undecided) {
+        d = cold_exact_decide(P, G, B.V, q1, q2, 2, P.choose_j_tar ? (target_reached_joint(P, q1, q2) ? 1 : 0) : 2);
+        if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
+        if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
+        if (RECORD) {                                                             // experiment_0.py:23-25
+            const int64_t o = hc->o;
+            __stcs(A.rec_j1 + o, (float)q1);
+            __stcs(A.rec_j2 + o, (float)q2);
+            __stcs(A.rec_reward + o, rw);
+            A.rec_flags[o] = (uint8_t)fl;
+        }
+        ++el;
+    }
+    if (d >> 2) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)(d >> 2));
+    if (fl) {                                                                     // experiment_0.py:30-34
+        atomicAdd(&s_acc[AG_ST_EPISODES], 1ull);
+        if (fl & AG_FLAG_COLLISION) atomicAdd(&s_acc[AG_ST_COLLISIONS], 1ull);
+        if (fl & AG_FLAG_DONE) atomicAdd(&s_acc[AG_ST_SUCCESSES], 1ull);
+        atomicAdd(&s_acc[AG_ST_EP_LEN_SUM], (unsigned long long)el);
+        atomicAdd(&s_acc[AG_ST_RETURN_MILLI], (unsigned long long)(long long)llrintf(rw * 1e-3f));
+        if (d & 1) {   // Scene.reset(): the pose is unchanged since the step, so collision_check() == (d & 1)
+            const int64_t e = hc->e;
+            const FastConst C = make_fast_const(P, G);
+            uint32_t rc = A.reset_ctr[e];
+            resample_pose<ENGINE, HAS_RESET_U, BP, false>(P, G, B, C, true, q1, q2, rc,
+                                                          HAS_RESET_U ? A.reset_u + e * A.R * 2 : nullptr, A.R, A.seed,
+                                                          (uint64_t)(A.env_id0 + e), s_acc);
+            A.reset_ctr[e] = rc;
+        }
+        rw = 0.0f; fl = 0; el = 0;                                                // scene_0.py:111-113
+    }
+    hc->q1 = q1; hc->q2 = q2; hc->rw = rw; hc->flags = fl; hc->el = el;
+    hc->t += 1; hc->o += A.row_stride;
+}
+
+// Two-level loop.  The inner loop is call-free: it runs steps until ANY lane of the warp has an
+// event -- an undecided float32 filter, an episode end, an axis-aligned evaluation -- then the
+// whole warp leaves it together, the affected lanes run cold_section(), and the warp re-enters
+// the inner loop in lockstep (same t in every lane: action loads and record stores stay coalesced).
 template <int ENGINE, int BP, bool HAS_ACT, bool HAS_RESET_U, bool RECORD>
-__global__ void __launch_bounds__(AG_BLOCK, ENGINE == AG_ENGINE_FAST ? (BP == BP_LIST ? 4 : 2) : 1)
-k_rollout(const ag_params P, const GridDev G, const RolloutDev A) {
+__global__ void __launch_bounds__(AG_BLOCK, ENGINE == AG_ENGINE_FAST ? (BP == BP_LIST ? AG_FAST_BLOCKS_PER_SM : 2) : 1)
+k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G, const __grid_constant__ FastConst C,
+          const __grid_constant__ RolloutDev A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ FastList s_fl;
     __shared__ unsigned long long s_acc[AG_ST_COUNT];
     if (threadIdx.x < AG_ST_COUNT) s_acc[threadIdx.x] = 0;
-    const BlockCtx B = block_prologue<ENGINE>(G, A.env_id0, A.n, smem, &s_fl);
+    const BlockCtx B0 = block_prologue<ENGINE>(G, A.env_id0, A.n, smem, &s_fl);
     __syncthreads();
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < A.n) {
-        const FastConst C = make_fast_const(P, G);
-        const uint64_t gid = (uint64_t)(A.env_id0 + e);
-        double q1 = A.j1[e], q2 = A.j2[e];
-        float rw = A.reward[e];
-        uint32_t fl = A.flags[e];
-        uint32_t sc = A.step_ctr[e], rc = A.reset_ctr[e], el = A.ep_len[e];
-        const float2 *act = HAS_ACT ? reinterpret_cast<const float2 *>(A.actions) + e : nullptr;
-        const double *ru = HAS_RESET_U ? A.reset_u + (int64_t)e * A.R * 2 : nullptr;
-        const float rw_coll = (float)P.reward_collision, rw_reach = (float)P.reward_reach;
-        int64_t o = e;
-        for (int t = 0; t < A.K; ++t, o += A.row_stride) {
-            double d1, d2;
-            if (HAS_ACT) {
-                const float2 a = __ldcs(act);                                // streamed once
-                act += A.row_stride;
-                d1 = (double)a.x; d2 = (double)a.y;
-            } else {
-                double u0, u1;
-                philox_uniform2(A.seed, gid, sc, 0u, u0, u1);
-                d1 = __dmul_rn(__dsub_rn(u0, 0.5), P.action_scale);          // scene_0.py:84
-                d2 = __dmul_rn(__dsub_rn(u1, 0.5), P.action_scale);          // :85
-            }
-            ++sc;
-            q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);                  // two_joint_robot.py:71-72
-            const int d = step_decide<ENGINE, BP>(P, G, B, C, q1, q2);
-            if (d & 1) { rw = rw_coll; fl |= AG_FLAG_COLLISION; }            // scene_0.py:95-97
-            if (d & 2) { rw = rw_reach; fl |= AG_FLAG_DONE; }                // :98-100
-            if (RECORD) {                                                    // experiment_0.py:23-25
-                __stcs(A.rec_j1 + o, (float)q1);
-                __stcs(A.rec_j2 + o, (float)q2);
-                __stcs(A.rec_reward + o, rw);
-                A.rec_flags[o] = (uint8_t)fl;
-            }
-            ++el;
-            if (fl | (d >> 2)) {                                             // experiment_0.py:30-34 (rare)
-                if (d >> 2) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)(d >> 2));
-                if (fl) {
-                    atomicAdd(&s_acc[AG_ST_EPISODES], 1ull);
-                    if (fl & AG_FLAG_COLLISION) atomicAdd(&s_acc[AG_ST_COLLISIONS], 1ull);
-                    if (fl & AG_FLAG_DONE) atomicAdd(&s_acc[AG_ST_SUCCESSES], 1ull);
-                    atomicAdd(&s_acc[AG_ST_EP_LEN_SUM], (unsigned long long)el);
-                    atomicAdd(&s_acc[AG_ST_RETURN_MILLI], (unsigned long long)(long long)llrintf(rw * 1e-3f));
-                    el = 0;
-                    // Scene.reset(): the pose is unchanged since the step, so collision_check() == (d & 1)
-                    resample_pose<ENGINE, HAS_RESET_U, BP, true>(P, G, B, C, (d & 1) != 0, q1, q2, rc, ru, A.R, A.seed, gid, s_acc);
-                    rw = 0.0f; fl = 0;                                       // scene_0.py:111-113
+    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e0 < A.n) {
+        HotCtx hc;
+        hc.q1 = A.j1[e0]; hc.q2 = A.j2[e0]; hc.rw = A.reward[e0]; hc.flags = A.flags[e0]; hc.el = A.ep_len[e0];
+        hc.act = HAS_ACT ? reinterpret_cast<const float2 *>(A.actions) + e0 : nullptr;
+        hc.a_next = make_float2(0.f, 0.f);
+        if (HAS_ACT) hc.a_next = __ldcs(hc.act);                                 // streamed once
+        hc.vbits = B0.V.bits; hc.vminx = B0.V.min_x; hc.vminy = B0.V.min_y; hc.fl = B0.fl;
+        hc.o = e0; hc.e = e0; hc.mask = __activemask(); hc.t = 0; hc.d = 0; hc.undecided = 0;
+        const uint32_t sc0 = A.step_ctr[e0];
+        A.step_ctr[e0] = sc0 + (uint32_t)A.K;
+        for (;;) {
+            // ---- hot state: struct -> registers ---------------------------------------------------
+            double q1 = hc.q1, q2 = hc.q2;
+            float rw = hc.rw;
+            uint32_t fl = hc.flags, el = hc.el;
+            const uint32_t warp_mask = hc.mask;
+            const float2 *act = hc.act;
+            float2 a_next = hc.a_next;
+            int64_t o = hc.o;
+            int t = hc.t, d = 0;
+            bool undecided = false;
+            BlockCtx B;
+            B.V.bits = hc.vbits; B.V.min_x = hc.vminx; B.V.min_y = hc.vminy; B.fl = hc.fl;
+            const uint64_t gid = (uint64_t)(A.env_id0 + hc.e);
+            const float rw_coll = (float)P.reward_collision, rw_reach = (float)P.reward_reach;
+#pragma unroll 1
+            for (; t < A.K; ++t, o += A.row_stride) {
+                double d1, d2;
+                if (HAS_ACT) {
+                    const float2 a = a_next;
+                    act += A.row_stride;
+                    if (t + 1 < A.K) a_next = __ldcs(act);                       // prefetch the next step's action
+                    d1 = (double)a.x; d2 = (double)a.y;
+                } else {
+                    double u0, u1;
+                    philox_uniform2(A.seed, gid, sc0 + (uint32_t)t, 0u, u0, u1);
+                    d1 = __dmul_rn(__dsub_rn(u0, 0.5), P.action_scale);          // scene_0.py:84
+                    d2 = __dmul_rn(__dsub_rn(u1, 0.5), P.action_scale);          // :85
                 }
+                q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);                  // two_joint_robot.py:71-72
+                if constexpr (ENGINE == AG_ENGINE_FAST) {
+                    d = fast_filter<BP>(P, G, B.V, B.fl, C, q1, q2);             // (c | r << 2), c,r in {0,1,2}
+                    undecided = ((d | (d >> 2)) & 2) != 0;
+                    d = (d & 1) | ((d >> 1) & 2);                                // -> bit0 collision, bit1 reached
+                } else {
+                    d = step_decide<ENGINE, BP>(P, G, B, C, q1, q2);
+                }
+                bool event = undecided;
+                if (!undecided) {
+                    if (d & 1) { rw = rw_coll; fl |= AG_FLAG_COLLISION; }        // scene_0.py:95-97
+                    if (d & 2) { rw = rw_reach; fl |= AG_FLAG_DONE; }            // :98-100
+                    if (RECORD) {                                                // experiment_0.py:23-25
+                        __stcs(A.rec_j1 + o, (float)q1);
+                        __stcs(A.rec_j2 + o, (float)q2);
+                        __stcs(A.rec_reward + o, rw);
+                        A.rec_flags[o] = (uint8_t)fl;
+                    }
+                    ++el;
+                    event = (fl | (d >> 2)) != 0;
+                }
+                if (__any_sync(warp_mask, event)) break;                         // warp-uniform exit
             }
+            // ---- registers -> struct ---------------------------------------------------------------
+            hc.q1 = q1; hc.q2 = q2; hc.rw = rw; hc.flags = fl; hc.el = el;
+            if (t >= A.K) break;
+            hc.act = act; hc.a_next = a_next; hc.o = o; hc.t = t; hc.d = d; hc.undecided = undecided ? 1 : 0;
+            if (undecided | ((fl | (d >> 2)) != 0))
+                cold_section<ENGINE, BP, HAS_RESET_U, RECORD>(P, G, A, &hc, s_acc);
+            else { hc.t = t + 1; hc.o = o + A.row_stride; }
         }
         atomicAdd(&s_acc[AG_ST_ENV_STEPS], (unsigned long long)A.K);
-        A.j1[e] = q1; A.j2[e] = q2; A.reward[e] = rw; A.flags[e] = (uint8_t)fl;
-        A.step_ctr[e] = sc; A.reset_ctr[e] = rc; A.ep_len[e] = el;
+        A.j1[e0] = hc.q1; A.j2[e0] = hc.q2; A.reward[e0] = hc.rw; A.flags[e0] = (uint8_t)hc.flags;
+        A.ep_len[e0] = hc.el;
     }
     stats_flush(s_acc, A.stats);
 }
@@ -406,7 +502,7 @@ ag_status launch_rollout_t(const ag_params &P, const GridDev &G, const RolloutDe
     auto k = k_rollout<E, BP, HA, HR, REC>;
     ag_status st = set_smem(k, smem);
     if (st) return st;
-    k<<<blocks_for(A.n), AG_BLOCK, smem, s>>>(P, G, A);
+    k<<<blocks_for(A.n), AG_BLOCK, smem, s>>>(P, G, make_fast_const(P, G), A);
     return launched();
 }
 
