@@ -16,6 +16,7 @@ from .._device import as_f64, ptr, require_cuda, stream_ptr
 from ..environment.occupancy_grid import BatchedOccupancyGrid, DeviceGrid, OccupancyGrid
 from ..robot.two_joint_robot import BatchedTwoJointRobot, TwoJointRobot
 from ..utils.geometry import Point
+from ..sharding import StatsReducer
 
 
 def _engine(e):
@@ -57,6 +58,7 @@ class BatchedScene:
         self.ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(_lib.ST_COUNT, dtype=torch.int64, device=dev)
         self._pipelines = {}
+        self._reducer = StatsReducer()
         self._lib = _lib.load()
 
     # ---- views with the reference's attribute names ---------------------------------------------
@@ -80,13 +82,17 @@ class BatchedScene:
     def stats_dict(self):
         return dict(zip(_lib.STAT_NAMES, self.stats.tolist()))
 
-    def all_reduce_stats(self):
-        """Sum the episode counters over ranks (the only collective on this path):
-        one int64[8] all-reduce on the stream the rollout kernel ran on."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.stats, op=dist.ReduceOp.SUM)
-        return self.stats
+    def all_reduce_stats(self, wait=True):
+        """Sum the episode counters over ranks (the only collective on this path): one
+        int64[8] all-reduce of a snapshot of this rank's cumulative counters, started asynchronously
+        so that it overlaps the next rollout launch.  Returns the global totals (wait=True) or
+        None (wait=False; fetch them later with global_stats())."""
+        self._reducer.submit(self.stats)
+        return self._reducer.result() if wait else None
+
+    def global_stats(self):
+        """Global cumulative counters of the newest all_reduce_stats() call."""
+        return self._reducer.result()
 
     # ---- K2 ------------------------------------------------------------------------------------
     def collision_check(self, first_hit=False, engine=None):

@@ -34,11 +34,40 @@ def init_from_env(backend=None):
 
 
 def all_reduce_stats(stats: torch.Tensor) -> torch.Tensor:
-    """In-place SUM of the int64 episode counters over all ranks (integer sums: order-independent,
-    so N-GPU totals equal the 1-GPU totals bit for bit)."""
+    """In-place SUM of int64 episode counters over all ranks (integer sums: order-independent,
+    so N-GPU totals equal the 1-GPU totals bit for bit).  Call it on a per-launch DELTA or on a
+    copy of the cumulative local counters -- never twice on the same cumulative buffer."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     return stats
+
+
+class StatsReducer:
+    """Global episode statistics of a sharded rollout without stalling the data path.
+
+    After every rollout launch `submit(local_stats)` snapshots this rank's cumulative counters
+    (stream-ordered after the kernel) and starts their all-reduce with async_op=True: NCCL runs it
+    on its own stream, so the next rollout kernel is not queued behind the collective.  `result()`
+    waits for the newest submitted reduction and returns the global cumulative totals."""
+
+    def __init__(self):
+        self._buf = None
+        self._work = None
+
+    def submit(self, local_stats: torch.Tensor) -> None:
+        if self._work is not None:
+            self._work.wait()                 # at most one reduction in flight; it overlapped the last kernel
+        buf = local_stats.clone()
+        self._buf = buf
+        self._work = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self._work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
+
+    def result(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self._buf
 
 
 def max_over_ranks(value: float, device=None) -> float:

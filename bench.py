@@ -124,14 +124,14 @@ def run_reference(args, rank, world):
     sq = orc.manual_grid()[0]
     st = orc.RolloutState(rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n))
     actions = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32) if args.mode == "record" else None
+    cores = host_cores()                             # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
     for _ in range(args.warmup):
-        orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record")
+        orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record")
+        orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
     dt = time.perf_counter() - t0
     value = n * K * args.steps / dt
-    cores = orc.num_threads()
     sample = "%d envs x %d env-steps per step (1/%d of one GPU's batch), OpenMP over envs" % (n, K, max(1, args.envs // n))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
@@ -143,6 +143,13 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def workload_config(args, world):
@@ -162,13 +169,14 @@ def cpu_baseline(args):
     sq = orc.manual_grid()[0]
     st = orc.RolloutState(rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n))
     actions = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32) if args.mode == "record" else None
-    orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record")
+    cores = host_cores()
+    orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
     reps, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < 10.0:
-        orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record")
+        orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
         reps += 1
     dt = time.perf_counter() - t0
-    return {"value": n * K * reps / dt, "unit": "env-steps/s", "cores": orc.num_threads(), "kind": "port",
+    return {"value": n * K * reps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
             "sample": "%d x (%d envs x %d env-steps), %.1f s, OpenMP over envs" % (reps, n, K, dt)}
 
 
@@ -177,7 +185,6 @@ def run_ours(args, rank, world, local):
     import torch
     import torch.distributed as dist
     import abstract_gym_b200 as ag
-    from abstract_gym_b200.sharding import all_reduce_stats
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -197,7 +204,7 @@ def run_ours(args, rank, world, local):
 
     def one_step():
         scene.rollout(K, actions=actions, record=record, out=rec)
-        all_reduce_stats(scene.stats)
+        scene.all_reduce_stats(wait=False)           # async: overlaps the next launch
 
     def barrier():
         if world > 1:
@@ -217,7 +224,8 @@ def run_ours(args, rank, world, local):
         a.record()                                   # same stream the kernel is launched on (torch current stream)
         scene.rollout(K, actions=actions, record=record, out=rec)
         b.record()
-        all_reduce_stats(scene.stats)
+        scene.all_reduce_stats(wait=False)
+    scene.global_stats()                             # the last reduction is inside the timed region
     stop.record()
     barrier()
     wall1 = time.time()
@@ -246,7 +254,8 @@ def run_ours(args, rank, world, local):
         t0 = time.perf_counter()
         for _ in range(reps):
             scene.rollout_host(K, hact, hout)        # returns after records + stats are in host memory
-            all_reduce_stats(scene.stats)
+            scene.all_reduce_stats(wait=False)
+        scene.global_stats()
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -258,7 +267,7 @@ def run_ours(args, rank, world, local):
                "d2h_bytes_per_step": (K * n * 13 if record else 0) + 8 * 8 * 3,
                "reps": reps, "ms_per_step": 1e3 * dt / reps,
                "api": "BatchedScene.rollout_host -> ag_rollout_host (pinned host buffers, 3-stream chunk pipeline)"}
-    stats = scene.stats_dict()
+    stats = dict(zip(ag.STAT_NAMES, scene.all_reduce_stats().tolist()))   # global totals over all ranks
     if rank != 0:
         return
     peak, peak_src = peaks()

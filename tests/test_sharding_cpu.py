@@ -56,7 +56,14 @@ def _worker(rank, world, port, out_dir):
     rec, stats = orc.rollout(st, K, [sq], env_id0=lo, seed=SEED, threads=1)
     t = torch.from_numpy(stats.copy())
     all_reduce_stats(t)
-    np.savez(os.path.join(out_dir, "r%d.npz" % rank), stats=t.numpy(), j1=st.j1, flags=rec["flags"], lo=lo, hi=hi)
+    # cumulative counters reduced after every launch (bench.py's pattern): no double counting
+    from abstract_gym_b200.sharding import StatsReducer
+    red, cum = StatsReducer(), torch.zeros(len(stats), dtype=torch.int64)
+    for _ in range(3):
+        cum += torch.from_numpy(stats)           # "launch" adds this rank's delta to its cumulative counters
+        red.submit(cum)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), stats=t.numpy(), j1=st.j1, flags=rec["flags"], lo=lo, hi=hi,
+             cum3=red.result().numpy())
     dist.destroy_process_group()
 
 
@@ -70,6 +77,7 @@ def test_two_rank_rollout_equals_single(tmp_path, oracle):
     parts = [np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(2)]
     for p in parts:
         assert np.array_equal(p["stats"], stats)          # all-reduced totals == single-process totals
+        assert np.array_equal(p["cum3"], 3 * stats)
         lo, hi = int(p["lo"]), int(p["hi"])
         assert np.array_equal(p["j1"], st.j1[lo:hi])      # per-env results do not depend on the sharding
         assert np.array_equal(p["flags"], rec["flags"][:, lo:hi])
