@@ -11,11 +11,13 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
+ABI_VERSION = 2
 ENGINE_EXACT, ENGINE_FAST, ENGINE_BRUTE = 0, 1, 2
 ENGINES = {"exact": ENGINE_EXACT, "fast": ENGINE_FAST, "brute": ENGINE_BRUTE}
 FLAG_COLLISION, FLAG_DONE = 1, 2
 ST_EPISODES, ST_COLLISIONS, ST_SUCCESSES, ST_ENV_STEPS, ST_EP_LEN_SUM, ST_RETURN_MILLI, \
     ST_STUCK_RESETS, ST_AXIS_ALIGNED, ST_COUNT = range(9)
+DIAG_NAMES = ("exact_steps", "cold_calls", "warp_exits")
 STAT_NAMES = ("episodes", "collisions", "successes", "env_steps", "ep_len_sum", "return_milli",
               "stuck_resets", "axis_aligned")
 
@@ -53,7 +55,7 @@ class RolloutArgs(C.Structure):
                 ("j1", C.c_void_p), ("j2", C.c_void_p), ("reward", C.c_void_p), ("flags", C.c_void_p),
                 ("step_ctr", C.c_void_p), ("reset_ctr", C.c_void_p), ("ep_len", C.c_void_p),
                 ("rec_j1", C.c_void_p), ("rec_j2", C.c_void_p), ("rec_reward", C.c_void_p),
-                ("rec_flags", C.c_void_p), ("stats", C.c_void_p)]
+                ("rec_flags", C.c_void_p), ("stats", C.c_void_p), ("diag", C.c_void_p)]
 
 
 # every symbol include/abstract_gym_b200.h declares: (restype, argtypes)
@@ -105,7 +107,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
         fn.restype, fn.argtypes = res, args
-    if lib.ag_abi_version() != 1:
+    if lib.ag_abi_version() != ABI_VERSION:
         raise ImportError("abstract_gym_b200: ABI version mismatch")
     _lib = lib
     return lib

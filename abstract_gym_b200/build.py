@@ -42,21 +42,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = None) -> str:
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("AG_NVCC_EXTRA", "").split()          # A/B builds, e.g. -DAG_ROLLOUT_SMALL_BLOCK=64
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    log = os.path.join(HERE, "build.log")
+    log = (out + ".log") if out else os.path.join(HERE, "build.log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed (%d); see %s" % (r.returncode, log))
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out))

@@ -38,6 +38,9 @@ constexpr float AG_M = 8.0e-7f;          // margin on (link coordinate - corner)
 constexpr float AG_K1 = 1.2e-6f;         // cross-product error coefficient (see narrow_f32)
 constexpr float AG_MIN_DXY = 1.0e-5f;    // below this |dx| or |dy| the filter refuses to decide
 constexpr int AG_LIST_MAX = 8;           // obstacle-list broad phase for grids with <= 8 occupied cells
+// Broad-phase margin of broad_list(): AG_M plus the rounding of its centre / half-extent arithmetic
+// (square centre 1.2e-7, link centre and half extent 1.2e-7 each, two subtractions 2.4e-7; |coordinates| < 2).
+constexpr float AG_M_BROAD = 2.0e-6f;
 
 struct ArmF { float ex, ey, gx, gy; };
 
@@ -53,46 +56,48 @@ __host__ __device__ __forceinline__ FastConst make_fast_const(const ag_params &P
     return C;
 }
 
-// sin(pi/2*f), cos(pi/2*f) for f in [-0.5, 0.5] (quarter turns); max abs error 9e-8
-// (near-minimax fits, checked against float64 on 2e6 points: DESIGN.md "FAST engine error budget").
-__device__ __forceinline__ void sincos_quarter(float f, float &s, float &c) {
+// sin(pi*f)/f and cos(pi*f) for f in [-0.5, 0.5] (half turns) as polynomials in u = f*f: degree-4
+// near-minimax fits (approximation error 1.4e-8 / 4.7e-8).  Evaluated in float32 the sine and cosine are
+// within 2.1e-7 of the float64 values, the link end points within 1.4e-7 m (4e6 random angles, emulated
+// op for op in numpy: DESIGN.md "FAST engine error budget"; measured on the GPU by test_fast_fk_error_budget).
+__device__ __forceinline__ void sincos_half(float f, float &s, float &c) {
     const float u = f * f;
-    float ps = -0.0046021631049598674f;
-    ps = fmaf(ps, u, 0.07968022285816816f);
-    ps = fmaf(ps, u, -0.6459634781534226f);
-    ps = fmaf(ps, u, 1.5707963219600267f);
+    float ps = 0.07765940576791763f;
+    ps = fmaf(ps, u, -0.5982921719551086f);
+    ps = fmaf(ps, u, 2.5500776767730713f);
+    ps = fmaf(ps, u, -5.167710304260254f);
+    ps = fmaf(ps, u, 3.1415927410125732f);
     s = ps * f;
-    float pc = 0.0009036298853670689f;
-    pc = fmaf(pc, u, -0.020860070409767503f);
-    pc = fmaf(pc, u, 0.2536692037972198f);
-    pc = fmaf(pc, u, -1.2337005406402657f);
-    c = fmaf(pc, u, 0.9999999999525445f);
+    float pc = 0.2196967899799347f;
+    pc = fmaf(pc, u, -1.3318802118301392f);
+    pc = fmaf(pc, u, 4.058412075042725f);
+    pc = fmaf(pc, u, -4.934792995452881f);
+    c = fmaf(pc, u, 0.9999999403953552f);
 }
 
-// float32 sin/cos of a float64 angle: j*(2/pi) and the rounding to the nearest quarter turn stay
-// in float64 (4 DP ops), the rest is float32.
-__device__ __forceinline__ void sincos_f32_of_f64(double j, float &s, float &c) {
-    const double t = j * 0.63661977236758134308;               // quarter turns
+// float32 (sin, cos) * len of a float64 angle.  The reduction to half turns (j/pi, round to nearest
+// integer k, remainder f) stays in float64 (3 DP ops); sin(j) = (-1)^k sin(pi f), cos(j) = (-1)^k cos(pi f),
+// and the sign is folded into the link length with one XOR, so there is no select on the ALU pipe.
+__device__ __forceinline__ void sincos_len_f32_of_f64(double j, float len, float &s_len, float &c_len) {
+    const double t = j * 0.31830988618379067154;               // half turns
     const double tk = t + 6755399441055744.0;                  // 1.5*2^52: rounds to nearest integer
-    const int k = __double2loint(tk);
+    const uint32_t k = (uint32_t)__double2loint(tk);
     const float f = (float)(t - (tk - 6755399441055744.0));
     float sq, cq;
-    sincos_quarter(f, sq, cq);
-    const float a = (k & 1) ? cq : sq, b = (k & 1) ? sq : cq;  // odd quadrant: swap
-    s = (k & 2) ? -a : a;                                      // q: 0:(s,c) 1:(c,-s) 2:(-s,-c) 3:(-c,s)
-    c = ((k + 1) & 2) ? -b : b;
+    sincos_half(f, sq, cq);
+    const float sl = __uint_as_float(__float_as_uint(len) ^ (k << 31));
+    s_len = sq * sl; c_len = cq * sl;
 }
 
-// ok=false when an angle is outside the range where the reduction above is trustworthy
+// ok=false when an angle is outside the range where the reduction above is trustworthy (also NaN)
 __device__ __forceinline__ ArmF fast_forward_kinematics(double j1, double j2, const FastConst &C, bool &ok) {
     float s1, c1, s2, c2;
-    sincos_f32_of_f64(j1, s1, c1);
-    sincos_f32_of_f64(j2, s2, c2);
-    // |j| < 2^20 rad, tested on the exponent fields (no float64 compare in the hot loop)
-    ok = (max(__double2hiint(j1) & 0x7FF00000, __double2hiint(j2) & 0x7FF00000) < ((1023 + 20) << 20));
+    sincos_len_f32_of_f64(j1, C.l1, s1, c1);
+    sincos_len_f32_of_f64(j2, C.l2, s2, c2);
+    ok = (fabs(j1) < 1048576.0) && (fabs(j2) < 1048576.0);     // two DSETP on the (idle) FP64 pipe
     ArmF a;
-    a.ex = c1 * C.l1; a.ey = s1 * C.l1;
-    a.gx = fmaf(c2, C.l2, a.ex); a.gy = fmaf(s2, C.l2, a.ey);
+    a.ex = c1; a.ey = s1;
+    a.gx = c2 + a.ex; a.gy = s2 + a.ey;
     return a;
 }
 
@@ -135,6 +140,8 @@ __device__ __forceinline__ int narrow_f32(const LinkF &L, float min_x, float min
 // Built per block in shared memory from the staged bit grid, row-major order.
 struct FastList {
     int m;                          // number of occupied cells, or -1 if the list form does not apply
+    float hm;                       // side/2 + AG_M_BROAD: centre-distance threshold of the broad phase
+    float2 ctr[AG_LIST_MAX];        // square centres as float32
     float4 sq[AG_LIST_MAX];         // (min_x, min_y, max_x, max_y) as float32
 };
 
@@ -161,13 +168,49 @@ __device__ __forceinline__ void build_fast_list(const GridDev &G, const GridView
                     const int c = __ffs(w) - 1;
                     w &= w - 1;
                     const float mnx = (float)V.min_x[c], mny = (float)V.min_y[lane];
+                    fl->ctr[slot] = make_float2(fmaf(0.5f, side, mnx), fmaf(0.5f, side, mny));
                     fl->sq[slot++] = make_float4(mnx, mny, mnx + side, mny + side);
                 }
             }
         }
-        if (lane == 0) fl->m = m;
+        if (lane == 0) { fl->m = m; fl->hm = fmaf(0.5f, (float)G.side, AG_M_BROAD); }
     }
     __syncthreads();
+}
+
+// Branch-free broad phase of the hot loop.  For link l (centre c_l, half extents h_l) and square k (centre o_k,
+// half side h): the closed boxes come within AG_M of each other  =>  max(|c_lx-o_kx| - h_lx, |c_ly-o_ky| - h_ly) < h + AG_M.
+// Returns the minimum of that measure over both links and all squares (compare with fl.hm).  8 FADD (FMA pipe)
+// + 2 FMNMX + 1 FMNMX3 (ALU pipe) per square; the loop is unrolled with warp-uniform guards.
+template <int M>
+__device__ __forceinline__ float broad_list_m(const FastList &fl, float c1x, float c1y, float c2x, float c2y, float h2x,
+                                              float h2y) {
+    float acc = 1.0e30f;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        const float2 o = fl.ctr[k];
+        const float m1 = fmaxf(fabsf(c1x - o.x) - fabsf(c1x), fabsf(c1y - o.y) - fabsf(c1y));
+        const float m2 = fmaxf(fabsf(c2x - o.x) - h2x, fabsf(c2y - o.y) - h2y);
+        acc = fminf(acc, fminf(m1, m2));
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float broad_list(const FastList &fl, const ArmF &a) {
+    const float c1x = 0.5f * a.ex, c1y = 0.5f * a.ey;                        // link 1: (0,0) -> elbow; half extents |c1|
+    const float c2x = fmaf(0.5f, a.gx, c1x), c2y = fmaf(0.5f, a.gy, c1y);    // link 2: elbow -> end effector
+    const float h2x = fabsf(c2x - a.ex), h2y = fabsf(c2y - a.ey);
+    switch (fl.m) {                                                          // warp-uniform: one straight-line body per count
+        case 1: return broad_list_m<1>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
+        case 2: return broad_list_m<2>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
+        case 3: return broad_list_m<3>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
+        case 4: return broad_list_m<4>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
+        case 5: return broad_list_m<5>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
+        case 6: return broad_list_m<6>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
+        case 7: return broad_list_m<7>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
+        case 8: return broad_list_m<8>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
+        default: return 1.0e30f;                                             // m == 0: nothing to hit; m < 0: caller sends every lane slow
+    }
 }
 
 // 0 / 1 certain, 2 undecided.  Warp-uniform loop over the (few) obstacles: range-overlap tests

@@ -31,6 +31,7 @@ struct RolloutDev {
     float *rec_j1, *rec_j2, *rec_reward;
     uint8_t *rec_flags;
     unsigned long long *stats;
+    unsigned long long *diag;
 };
 
 // ------------------------------------------------------------------------- per-block context
@@ -283,7 +284,7 @@ __device__ __forceinline__ int step_decide(const ag_params &P, const GridDev &G,
 }
 
 // Everything thread-private that the hot loop carries.  It lives in registers inside the inner
-// loop and is spilled to this struct (local memory) only around the out-of-line cold section, so
+// loops and is spilled to this struct (local memory) only around the out-of-line cold section, so
 // that no value is live across the ABI call: that is what keeps the inner loop spill-free under a
 // 64-register budget (DESIGN.md "register allocation of K4").
 struct HotCtx {
@@ -296,9 +297,21 @@ struct HotCtx {
     int64_t e;               // env index within the launch
     float2 a_next;
     float rw;
-    uint32_t flags, el, mask;
+    uint32_t flags, mask;
+    int el_off;              // episode length after step t = el_off + t + 1
     int t, d, undecided;
 };
+
+// one step record (experiment_0.py:23-25): joint_1, joint_2, step_reward, flags, post-step / pre-reset
+template <bool RECORD>
+__device__ __forceinline__ void store_record(const RolloutDev &A, int64_t o, double q1, double q2, float rw, uint32_t fl) {
+    if (RECORD) {
+        __stcs(A.rec_j1 + o, (float)q1);
+        __stcs(A.rec_j2 + o, (float)q2);
+        __stcs(A.rec_reward + o, rw);
+        A.rec_flags[o] = (uint8_t)fl;
+    }
+}
 
 // Cold section, out of line: (1) finish a step whose float32 filter was undecided with the
 // float64 reference arithmetic, (2) episode end (experiment_0.py:30-34): statistics + Scene.reset().
@@ -307,29 +320,23 @@ __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, 
                                           unsigned long long *s_acc) {
     double q1 = hc->q1, q2 = hc->q2;
     float rw = hc->rw;
-    uint32_t fl = hc->flags, el = hc->el;
+    uint32_t fl = hc->flags;
     int d = hc->d;
     BlockCtx B;
     B.V.bits = hc->vbits; B.V.min_x = hc->vminx; B.V.min_y = hc->vminy; B.fl = hc->fl;
     if (hc->undecided) {
+        atomicAdd(&s_acc[AG_ST_COUNT + AG_DIAG_EXACT_STEPS], 1ull);
         d = cold_exact_decide(P, G, B.V, q1, q2, 2, P.choose_j_tar ? (target_reached_joint(P, q1, q2) ? 1 : 0) : 2);
         if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
         if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
-        if (RECORD) {                                                             // experiment_0.py:23-25
-            const int64_t o = hc->o;
-            __stcs(A.rec_j1 + o, (float)q1);
-            __stcs(A.rec_j2 + o, (float)q2);
-            __stcs(A.rec_reward + o, rw);
-            A.rec_flags[o] = (uint8_t)fl;
-        }
-        ++el;
+        store_record<RECORD>(A, hc->o, q1, q2, rw, fl);                           // experiment_0.py:23-25
     }
     if (d >> 2) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)(d >> 2));
     if (fl) {                                                                     // experiment_0.py:30-34
         atomicAdd(&s_acc[AG_ST_EPISODES], 1ull);
         if (fl & AG_FLAG_COLLISION) atomicAdd(&s_acc[AG_ST_COLLISIONS], 1ull);
         if (fl & AG_FLAG_DONE) atomicAdd(&s_acc[AG_ST_SUCCESSES], 1ull);
-        atomicAdd(&s_acc[AG_ST_EP_LEN_SUM], (unsigned long long)el);
+        atomicAdd(&s_acc[AG_ST_EP_LEN_SUM], (unsigned long long)(uint32_t)(hc->el_off + hc->t + 1));
         atomicAdd(&s_acc[AG_ST_RETURN_MILLI], (unsigned long long)(long long)llrintf(rw * 1e-3f));
         if (d & 1) {   // Scene.reset(): the pose is unchanged since the step, so collision_check() == (d & 1)
             const int64_t e = hc->e;
@@ -340,30 +347,41 @@ __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, 
                                                           (uint64_t)(A.env_id0 + e), s_acc);
             A.reset_ctr[e] = rc;
         }
-        rw = 0.0f; fl = 0; el = 0;                                                // scene_0.py:111-113
+        rw = 0.0f; fl = 0; hc->el_off = -(hc->t + 1);                             // scene_0.py:111-113
     }
-    hc->q1 = q1; hc->q2 = q2; hc->rw = rw; hc->flags = fl; hc->el = el;
+    hc->q1 = q1; hc->q2 = q2; hc->rw = rw; hc->flags = fl;
     hc->t += 1; hc->o += A.row_stride;
 }
 
-// Two-level loop.  The inner loop is call-free: it runs steps until ANY lane of the warp has an
-// event -- an undecided float32 filter, an episode end, an axis-aligned evaluation -- then the
-// whole warp leaves it together, the affected lanes run cold_section(), and the warp re-enters
-// the inner loop in lockstep (same t in every lane: action loads and record stores stay coalesced).
-template <int ENGINE, int BP, bool HAS_ACT, bool HAS_RESET_U, bool RECORD>
-__global__ void __launch_bounds__(AG_BLOCK, ENGINE == AG_ENGINE_FAST ? (BP == BP_LIST ? AG_FAST_BLOCKS_PER_SM : 2) : 1)
+// Three nested loops, warp-synchronous (every lane of a warp is at the same step t, so action loads and
+// record stores stay coalesced):
+//   inner  : uneventful steps only -- float32 FK, broad_list(), the reach pre-test and the record of
+//            an uneventful step (reward 0, flags 0); branch-free, call-free, ~150 instructions that stay
+//            resident in the instruction cache.  A lane is "slow" when a link's box comes within the margin
+//            of a square, the end effector is within the margin of the target box, its angles are out of the
+//            filter's range or its sticky state is not clean; the warp leaves the loop when ANY lane is slow.
+//   middle : the narrow phase for the slow lanes (inline, placed after the inner loop); if no lane has an
+//            event -- collision, target reached, undecided filter, axis-aligned evaluation -- the warp
+//            goes straight back into the inner loop.
+//   outer  : event lanes run the out-of-line cold_section() (the only call; registers are exchanged
+//            through HotCtx), then the warp re-enters in lockstep.
+// Engines without the obstacle list (traversal, EXACT, BRUTE) have no pre-test: every step is "slow".
+template <int ENGINE, int BP, bool HAS_ACT, bool HAS_RESET_U, bool RECORD, bool FULL, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (ENGINE == AG_ENGINE_FAST ? (BP == BP_LIST ? AG_FAST_BLOCKS_PER_SM : 2) : 1) * (AG_BLOCK / BLOCK))
 k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G, const __grid_constant__ FastConst C,
           const __grid_constant__ RolloutDev A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ FastList s_fl;
-    __shared__ unsigned long long s_acc[AG_ST_COUNT];
-    if (threadIdx.x < AG_ST_COUNT) s_acc[threadIdx.x] = 0;
+    __shared__ unsigned long long s_acc[AG_ST_COUNT + AG_DIAG_COUNT];
+    if (threadIdx.x < AG_ST_COUNT + AG_DIAG_COUNT) s_acc[threadIdx.x] = 0;
     const BlockCtx B0 = block_prologue<ENGINE>(G, A.env_id0, A.n, smem, &s_fl);
     __syncthreads();
+    constexpr bool LIST = (ENGINE == AG_ENGINE_FAST && BP == BP_LIST);
     const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e0 < A.n) {
         HotCtx hc;
-        hc.q1 = A.j1[e0]; hc.q2 = A.j2[e0]; hc.rw = A.reward[e0]; hc.flags = A.flags[e0]; hc.el = A.ep_len[e0];
+        hc.q1 = A.j1[e0]; hc.q2 = A.j2[e0]; hc.rw = A.reward[e0]; hc.flags = A.flags[e0];
+        hc.el_off = (int)A.ep_len[e0];
         hc.act = HAS_ACT ? reinterpret_cast<const float2 *>(A.actions) + e0 : nullptr;
         hc.a_next = make_float2(0.f, 0.f);
         if (HAS_ACT) hc.a_next = __ldcs(hc.act);                                 // streamed once
@@ -371,71 +389,100 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
         hc.o = e0; hc.e = e0; hc.mask = __activemask(); hc.t = 0; hc.d = 0; hc.undecided = 0;
         const uint32_t sc0 = A.step_ctr[e0];
         A.step_ctr[e0] = sc0 + (uint32_t)A.K;
-        for (;;) {
-            // ---- hot state: struct -> registers ---------------------------------------------------
+        const float reach_thr_clean = C.reach_eps + (AG_DELTA_P + 2.0e-7f);      // reach_fast()'s margin
+        for (;;) {                                                               // ---- outer
+            // hot state: struct -> registers
             double q1 = hc.q1, q2 = hc.q2;
             float rw = hc.rw;
-            uint32_t fl = hc.flags, el = hc.el;
-            const uint32_t warp_mask = hc.mask;
+            uint32_t fl = hc.flags;
+            const uint32_t warp_mask = FULL ? 0xFFFFFFFFu : hc.mask;   // FULL: n % 32 == 0, every warp is complete
             const float2 *act = hc.act;
             float2 a_next = hc.a_next;
             int64_t o = hc.o;
             int t = hc.t, d = 0;
-            bool undecided = false;
+            bool undecided = false, event = false;
+            // a lane whose sticky state is not clean (flags / reward left by earlier step() calls) is
+            // forced through the slow branch: an infinite threshold makes its reach pre-test fire
+            float reach_thr = ((fl != 0) | (rw != 0.0f)) ? __int_as_float(0x7f800000) : reach_thr_clean;
             BlockCtx B;
-            B.V.bits = hc.vbits; B.V.min_x = hc.vminx; B.V.min_y = hc.vminy; B.fl = hc.fl;
+            B.V.bits = hc.vbits; B.V.min_x = hc.vminx; B.V.min_y = hc.vminy; B.fl = LIST ? &s_fl : hc.fl;
             const uint64_t gid = (uint64_t)(A.env_id0 + hc.e);
-            const float rw_coll = (float)P.reward_collision, rw_reach = (float)P.reward_reach;
+            for (;;) {                                                           // ---- middle
+                bool slow = true, ok = true;
+                ArmF a;
 #pragma unroll 1
-            for (; t < A.K; ++t, o += A.row_stride) {
-                double d1, d2;
-                if (HAS_ACT) {
-                    const float2 a = a_next;
-                    act += A.row_stride;
-                    if (t + 1 < A.K) a_next = __ldcs(act);                       // prefetch the next step's action
-                    d1 = (double)a.x; d2 = (double)a.y;
-                } else {
-                    double u0, u1;
-                    philox_uniform2(A.seed, gid, sc0 + (uint32_t)t, 0u, u0, u1);
-                    d1 = __dmul_rn(__dsub_rn(u0, 0.5), P.action_scale);          // scene_0.py:84
-                    d2 = __dmul_rn(__dsub_rn(u1, 0.5), P.action_scale);          // :85
-                }
-                q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);                  // two_joint_robot.py:71-72
-                if constexpr (ENGINE == AG_ENGINE_FAST) {
-                    d = fast_filter<BP>(P, G, B.V, B.fl, C, q1, q2);             // (c | r << 2), c,r in {0,1,2}
-                    undecided = ((d | (d >> 2)) & 2) != 0;
-                    d = (d & 1) | ((d >> 1) & 2);                                // -> bit0 collision, bit1 reached
-                } else {
-                    d = step_decide<ENGINE, BP>(P, G, B, C, q1, q2);
-                }
-                bool event = undecided;
-                if (!undecided) {
-                    if (d & 1) { rw = rw_coll; fl |= AG_FLAG_COLLISION; }        // scene_0.py:95-97
-                    if (d & 2) { rw = rw_reach; fl |= AG_FLAG_DONE; }            // :98-100
-                    if (RECORD) {                                                // experiment_0.py:23-25
-                        __stcs(A.rec_j1 + o, (float)q1);
-                        __stcs(A.rec_j2 + o, (float)q2);
-                        __stcs(A.rec_reward + o, rw);
-                        A.rec_flags[o] = (uint8_t)fl;
+                for (; t < A.K; ++t, o += A.row_stride) {                        // ---- inner
+                    double d1, d2;
+                    if (HAS_ACT) {
+                        const float2 an = a_next;
+                        act += A.row_stride;
+                        if (t + 1 < A.K) a_next = __ldcs(act);                   // prefetch the next step's action
+                        d1 = (double)an.x; d2 = (double)an.y;
+                    } else {
+                        double u0, u1;
+                        philox_uniform2(A.seed, gid, sc0 + (uint32_t)t, 0u, u0, u1);
+                        d1 = __dmul_rn(__dsub_rn(u0, 0.5), P.action_scale);      // scene_0.py:84
+                        d2 = __dmul_rn(__dsub_rn(u1, 0.5), P.action_scale);      // :85
                     }
-                    ++el;
-                    event = (fl | (d >> 2)) != 0;
+                    q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);              // two_joint_robot.py:71-72
+                    if constexpr (LIST) {
+                        a = fast_forward_kinematics(q1, q2, C, ok);
+                        const float sep = broad_list(s_fl, a);
+                        const float worst = fmaxf(fabsf(C.tx - a.gx), fabsf(C.ty - a.gy));
+                        slow = !(sep >= s_fl.hm) | !(worst >= reach_thr) | !ok | (s_fl.m < 0);   // NaN-safe: NaN is slow
+                        if (P.choose_j_tar) slow |= target_reached_joint(P, q1, q2);
+                        store_record<RECORD>(A, o, q1, q2, 0.0f, 0u);            // an uneventful step; slow lanes rewrite theirs
+                    }
+                    if (__any_sync(warp_mask, slow)) break;
                 }
-                if (__any_sync(warp_mask, event)) break;                         // warp-uniform exit
+                if (t >= A.K) break;
+                event = false;
+                if (slow) {
+                    if constexpr (LIST) {
+                        const int c = (ok && s_fl.m >= 0) ? arm_fast_list(&s_fl, a, C) : 2;
+                        int r;
+                        if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
+                        else r = ok ? reach_fast(C, a) : 2;
+                        undecided = ((c | r) & 2) != 0;
+                        d = (c & 1) | ((r & 1) << 1);
+                    } else if constexpr (ENGINE == AG_ENGINE_FAST) {
+                        d = fast_filter<BP>(P, G, B.V, B.fl, C, q1, q2);         // (c | r << 2), c,r in {0,1,2}
+                        undecided = ((d | (d >> 2)) & 2) != 0;
+                        d = (d & 1) | ((d >> 1) & 2);                            // -> bit0 collision, bit1 reached
+                    } else {
+                        d = step_decide<ENGINE, BP>(P, G, B, C, q1, q2);
+                    }
+                    event = undecided;
+                    if (!undecided) {
+                        if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
+                        if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
+                        store_record<RECORD>(A, o, q1, q2, rw, fl);                                // experiment_0.py:23-25
+                        event = (fl | (d >> 2)) != 0;
+                        reach_thr = (rw != 0.0f) ? __int_as_float(0x7f800000) : reach_thr_clean;
+                    }
+                }
+                if (__any_sync(warp_mask, event)) break;                         // warp-uniform exit to the cold section
+                ++t; o += A.row_stride;
             }
-            // ---- registers -> struct ---------------------------------------------------------------
-            hc.q1 = q1; hc.q2 = q2; hc.rw = rw; hc.flags = fl; hc.el = el;
+            // registers -> struct
+            hc.q1 = q1; hc.q2 = q2; hc.rw = rw; hc.flags = fl;
             if (t >= A.K) break;
             hc.act = act; hc.a_next = a_next; hc.o = o; hc.t = t; hc.d = d; hc.undecided = undecided ? 1 : 0;
-            if (undecided | ((fl | (d >> 2)) != 0))
+            if (event) {
+                atomicAdd(&s_acc[AG_ST_COUNT + AG_DIAG_COLD_CALLS], 1ull);
                 cold_section<ENGINE, BP, HAS_RESET_U, RECORD>(P, G, A, &hc, s_acc);
-            else { hc.t = t + 1; hc.o = o + A.row_stride; }
+            } else { hc.t = t + 1; hc.o = o + A.row_stride; }
+            if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[AG_ST_COUNT + AG_DIAG_WARP_EXITS], 1ull);
         }
         atomicAdd(&s_acc[AG_ST_ENV_STEPS], (unsigned long long)A.K);
         A.j1[e0] = hc.q1; A.j2[e0] = hc.q2; A.reward[e0] = hc.rw; A.flags[e0] = (uint8_t)hc.flags;
-        A.ep_len[e0] = hc.el;
+        A.ep_len[e0] = (uint32_t)(hc.el_off + A.K);
     }
     stats_flush(s_acc, A.stats);
+    if (A.diag != nullptr && threadIdx.x < AG_DIAG_COUNT) {
+        const unsigned long long v = s_acc[AG_ST_COUNT + threadIdx.x];
+        if (v != 0) atomicAdd(&A.diag[threadIdx.x], v);
+    }
 }
 
 // ------------------------------------------------------------------------------------- host side
@@ -497,13 +544,35 @@ inline unsigned blocks_for(int64_t n) { return (unsigned)((n + AG_BLOCK - 1) / A
         default: return AG_ERR_MODE;                                      \
     }
 
-template <int E, int BP, bool HA, bool HR, bool REC>
-ag_status launch_rollout_t(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s) {
-    auto k = k_rollout<E, BP, HA, HR, REC>;
+template <int E, int BP, bool HA, bool HR, bool REC, bool FULL, int BLOCK>
+ag_status launch_rollout_b(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s) {
+    auto k = k_rollout<E, BP, HA, HR, REC, FULL, BLOCK>;
     ag_status st = set_smem(k, smem);
     if (st) return st;
-    k<<<blocks_for(A.n), AG_BLOCK, smem, s>>>(P, G, make_fast_const(P, G), A);
+    k<<<(unsigned)((A.n + BLOCK - 1) / BLOCK), BLOCK, smem, s>>>(P, G, make_fast_const(P, G), A);
     return launched();
+}
+
+// Block size of the rollout kernel.  A block lasts as long as its slowest warp (cold-section visits are
+// Poisson-distributed per warp), and a finished warp's slot stays idle until the block retires, so
+// scene_0-class launches (obstacle list: per-block set-up is ~100 instructions) use one-warp blocks;
+// 256 threads remain for staged per-batch grids, where a block shares one shared-memory copy.
+constexpr int AG_SMALL_BLOCK =
+#ifdef AG_ROLLOUT_SMALL_BLOCK
+    AG_ROLLOUT_SMALL_BLOCK;
+#else
+    32;
+#endif
+
+template <int E, int BP, bool HA, bool HR, bool REC>
+ag_status launch_rollout_t(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s) {
+    if (E == AG_ENGINE_FAST && BP == BP_LIST && G.n_grids == 1) {
+        // complete warps only (n % 32 == 0): the warp votes use a constant full mask
+        if (A.n % 32 == 0)
+            return launch_rollout_b<E, BP, HA, HR, REC, E == AG_ENGINE_FAST && BP == BP_LIST, AG_SMALL_BLOCK>(P, G, A, smem, s);
+        return launch_rollout_b<E, BP, HA, HR, REC, false, AG_SMALL_BLOCK>(P, G, A, smem, s);
+    }
+    return launch_rollout_b<E, BP, HA, HR, REC, false, AG_BLOCK>(P, G, A, smem, s);
 }
 
 template <int E, int BP>
@@ -543,6 +612,7 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
     A.step_ctr = a->step_ctr; A.reset_ctr = a->reset_ctr; A.ep_len = a->ep_len;
     A.rec_j1 = a->rec_j1; A.rec_j2 = a->rec_j2; A.rec_reward = a->rec_reward; A.rec_flags = a->rec_flags;
     A.stats = reinterpret_cast<unsigned long long *>(a->stats);
+    A.diag = reinterpret_cast<unsigned long long *>(a->diag);
     cudaStream_t s = (cudaStream_t)stream;
     // FAST engine: the obstacle-list broad phase when the caller vouches for small sparse staged grids
     // (ag_grid.max_occupied); a block whose grid turns out not to qualify falls back to EXACT per lane.

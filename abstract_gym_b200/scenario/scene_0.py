@@ -57,6 +57,7 @@ class BatchedScene:
         self.reset_ctr = torch.zeros(n, dtype=torch.int32, device=dev)
         self.ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(_lib.ST_COUNT, dtype=torch.int64, device=dev)
+        self.diag = torch.zeros(len(_lib.DIAG_NAMES), dtype=torch.int64, device=dev)   # FAST-filter diagnostics
         self._pipelines = {}
         self._reducer = StatsReducer()
         self._lib = _lib.load()
@@ -81,6 +82,10 @@ class BatchedScene:
 
     def stats_dict(self):
         return dict(zip(_lib.STAT_NAMES, self.stats.tolist()))
+
+    def diag_dict(self):
+        """FAST-engine diagnostics accumulated by rollout(): float64 re-evaluations, cold-section visits, warp exits."""
+        return dict(zip(_lib.DIAG_NAMES, self.diag.tolist()))
 
     def all_reduce_stats(self, wait=True):
         """Sum the episode counters over ranks (the only collective on this path): one
@@ -185,6 +190,7 @@ class BatchedScene:
             a.rec_j1, a.rec_j2 = rec["j1"].data_ptr(), rec["j2"].data_ptr()
             a.rec_reward, a.rec_flags = rec["reward"].data_ptr(), rec["flags"].data_ptr()
         a.stats = self.stats.data_ptr()
+        a.diag = self.diag.data_ptr()
         return a
 
     def alloc_records(self, K, pinned_host=False):

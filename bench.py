@@ -284,7 +284,7 @@ def run_ours(args, rank, world, local):
                      "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
                      "peak_source": peak_src, "bytes_per_env_step": b_alg, "kernel_ms": kern_ms,
                      "kernel": "k_rollout", "note": "compute-bound path: see DESIGN.md roofline section"},
-        "clocks": clocks, "episode_stats": stats,
+        "clocks": clocks, "episode_stats": stats, "filter_diag_rank0": scene.diag_dict(),
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)

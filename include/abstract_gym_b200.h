@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AG_ABI_VERSION 1
+#define AG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define AG_API __attribute__((visibility("default")))
@@ -102,6 +102,14 @@ enum {
     AG_ST_STUCK_RESETS,      /* resets that exhausted max_reset_tries / the candidate list */
     AG_ST_AXIS_ALIGNED,      /* check_sections a==0/b==0 evaluations (AttributeError in the reference) */
     AG_ST_COUNT
+};
+
+/* FAST-engine diagnostics of ag_rollout (not part of the reference's semantics; ag_rollout_args.diag) */
+enum {
+    AG_DIAG_EXACT_STEPS = 0, /* env-steps whose float32 filter was undecided and that were re-evaluated in float64 */
+    AG_DIAG_COLD_CALLS,      /* lane visits of the out-of-line section (undecided steps + episode ends) */
+    AG_DIAG_WARP_EXITS,      /* times a warp left the call-free inner loop */
+    AG_DIAG_COUNT
 };
 
 /* ---- host-only helpers (no device needed) ------------------------------------------------- */
@@ -183,6 +191,7 @@ typedef struct ag_rollout_args {
     float *rec_j1, *rec_j2, *rec_reward;
     uint8_t *rec_flags;
     int64_t *stats;
+    int64_t *diag;           /* optional int64[AG_DIAG_COUNT] filter diagnostics (accumulated), or NULL */
 } ag_rollout_args;
 
 AG_API ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream);
