@@ -181,36 +181,21 @@ __device__ __forceinline__ void build_fast_list(const GridDev &G, const GridView
 // Branch-free broad phase of the hot loop.  For link l (centre c_l, half extents h_l) and square k (centre o_k,
 // half side h): the closed boxes come within AG_M of each other  =>  max(|c_lx-o_kx| - h_lx, |c_ly-o_ky| - h_ly) < h + AG_M.
 // Returns the minimum of that measure over both links and all squares (compare with fl.hm).  8 FADD (FMA pipe)
-// + 2 FMNMX + 1 FMNMX3 (ALU pipe) per square; the loop is unrolled with warp-uniform guards.
-template <int M>
-__device__ __forceinline__ float broad_list_m(const FastList &fl, float c1x, float c1y, float c2x, float c2y, float h2x,
-                                              float h2y) {
+// + 2 FMNMX + 1 FMNMX3 (ALU pipe) per square.
+__device__ __forceinline__ float broad_list(const FastList &fl, const ArmF &a) {
+    const float c1x = 0.5f * a.ex, c1y = 0.5f * a.ey;                        // link 1: (0,0) -> elbow; half extents |c1|
+    const float c2x = fmaf(0.5f, a.gx, c1x), c2y = fmaf(0.5f, a.gy, c1y);    // link 2: elbow -> end effector
+    const float h2x = fabsf(c2x - a.ex), h2y = fabsf(c2y - a.ey);
+    const int m = fl.m;
     float acc = 1.0e30f;
-#pragma unroll
-    for (int k = 0; k < M; ++k) {
+#pragma unroll 1
+    for (int k = 0; k < m; ++k) {            // warp-uniform trip count; kept rolled so the hot loop stays compact
         const float2 o = fl.ctr[k];
         const float m1 = fmaxf(fabsf(c1x - o.x) - fabsf(c1x), fabsf(c1y - o.y) - fabsf(c1y));
         const float m2 = fmaxf(fabsf(c2x - o.x) - h2x, fabsf(c2y - o.y) - h2y);
         acc = fminf(acc, fminf(m1, m2));
     }
     return acc;
-}
-
-__device__ __forceinline__ float broad_list(const FastList &fl, const ArmF &a) {
-    const float c1x = 0.5f * a.ex, c1y = 0.5f * a.ey;                        // link 1: (0,0) -> elbow; half extents |c1|
-    const float c2x = fmaf(0.5f, a.gx, c1x), c2y = fmaf(0.5f, a.gy, c1y);    // link 2: elbow -> end effector
-    const float h2x = fabsf(c2x - a.ex), h2y = fabsf(c2y - a.ey);
-    switch (fl.m) {                                                          // warp-uniform: one straight-line body per count
-        case 1: return broad_list_m<1>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
-        case 2: return broad_list_m<2>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
-        case 3: return broad_list_m<3>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
-        case 4: return broad_list_m<4>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
-        case 5: return broad_list_m<5>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
-        case 6: return broad_list_m<6>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
-        case 7: return broad_list_m<7>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
-        case 8: return broad_list_m<8>(fl, c1x, c1y, c2x, c2y, h2x, h2y);
-        default: return 1.0e30f;                                             // m == 0: nothing to hit; m < 0: caller sends every lane slow
-    }
 }
 
 // 0 / 1 certain, 2 undecided.  Warp-uniform loop over the (few) obstacles: range-overlap tests

@@ -408,8 +408,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
             B.V.bits = hc.vbits; B.V.min_x = hc.vminx; B.V.min_y = hc.vminy; B.fl = LIST ? &s_fl : hc.fl;
             const uint64_t gid = (uint64_t)(A.env_id0 + hc.e);
             for (;;) {                                                           // ---- middle
-                bool slow = true, ok = true;
-                ArmF a;
+                bool slow = true;
 #pragma unroll 1
                 for (; t < A.K; ++t, o += A.row_stride) {                        // ---- inner
                     double d1, d2;
@@ -426,7 +425,8 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                     }
                     q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);              // two_joint_robot.py:71-72
                     if constexpr (LIST) {
-                        a = fast_forward_kinematics(q1, q2, C, ok);
+                        bool ok;
+                        const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
                         const float sep = broad_list(s_fl, a);
                         const float worst = fmaxf(fabsf(C.tx - a.gx), fabsf(C.ty - a.gy));
                         slow = !(sep >= s_fl.hm) | !(worst >= reach_thr) | !ok | (s_fl.m < 0);   // NaN-safe: NaN is slow
@@ -439,6 +439,8 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                 event = false;
                 if (slow) {
                     if constexpr (LIST) {
+                        bool ok;                                                 // recomputed (identical values): cheaper than
+                        const ArmF a = fast_forward_kinematics(q1, q2, C, ok);   // keeping the arm live out of the inner loop
                         const int c = (ok && s_fl.m >= 0) ? arm_fast_list(&s_fl, a, C) : 2;
                         int r;
                         if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
