@@ -143,6 +143,8 @@ struct FastList {
     float hm;                       // side/2 + AG_M_BROAD: centre-distance threshold of the broad phase
     float2 ctr[AG_LIST_MAX];        // square centres as float32
     float4 sq[AG_LIST_MAX];         // (min_x, min_y, max_x, max_y) as float32
+    int cell[AG_LIST_MAX];          // (row << 16) | col
+    const double *vmin_x, *vmin_y;  // the block's float64 corner tables (second-level filter)
 };
 
 // warp 0 builds the list (S <= 32: one row word per lane)
@@ -169,11 +171,13 @@ __device__ __forceinline__ void build_fast_list(const GridDev &G, const GridView
                     w &= w - 1;
                     const float mnx = (float)V.min_x[c], mny = (float)V.min_y[lane];
                     fl->ctr[slot] = make_float2(fmaf(0.5f, side, mnx), fmaf(0.5f, side, mny));
+                    fl->cell[slot] = (lane << 16) | c;
                     fl->sq[slot++] = make_float4(mnx, mny, mnx + side, mny + side);
                 }
             }
         }
-        if (lane == 0) { fl->m = m; fl->hm = fmaf(0.5f, (float)G.side, AG_M_BROAD); }
+        // m < 0 (list form does not apply): an infinite threshold sends every lane through the slow branch
+        if (lane == 0) { fl->vmin_x = V.min_x; fl->vmin_y = V.min_y; fl->m = m; fl->hm = m < 0 ? __int_as_float(0x7f800000) : fmaf(0.5f, (float)G.side, AG_M_BROAD); }
     }
     __syncthreads();
 }
@@ -182,35 +186,54 @@ __device__ __forceinline__ void build_fast_list(const GridDev &G, const GridView
 // half side h): the closed boxes come within AG_M of each other  =>  max(|c_lx-o_kx| - h_lx, |c_ly-o_ky| - h_ly) < h + AG_M.
 // Returns the minimum of that measure over both links and all squares (compare with fl.hm).  8 FADD (FMA pipe)
 // + 2 FMNMX + 1 FMNMX3 (ALU pipe) per square.
+struct ArmBoxes { float c1x, c1y, c2x, c2y, h2x, h2y; };      // link centres; half extents: link 1 = |c1|, link 2 = h2
+
+__device__ __forceinline__ ArmBoxes make_arm_boxes(const ArmF &a) {
+    ArmBoxes b;
+    b.c1x = 0.5f * a.ex; b.c1y = 0.5f * a.ey;                                // link 1: (0,0) -> elbow
+    b.c2x = fmaf(0.5f, a.gx, b.c1x); b.c2y = fmaf(0.5f, a.gy, b.c1y);        // link 2: elbow -> end effector
+    b.h2x = fabsf(b.c2x - a.ex); b.h2y = fabsf(b.c2y - a.ey);
+    return b;
+}
+
+// separation measures of both links against the square centred at o (compare with FastList::hm)
+__device__ __forceinline__ void box_measures(const ArmBoxes &b, float2 o, float &m1, float &m2) {
+    m1 = fmaxf(fabsf(b.c1x - o.x) - fabsf(b.c1x), fabsf(b.c1y - o.y) - fabsf(b.c1y));
+    m2 = fmaxf(fabsf(b.c2x - o.x) - b.h2x, fabsf(b.c2y - o.y) - b.h2y);
+}
+
 __device__ __forceinline__ float broad_list(const FastList &fl, const ArmF &a) {
-    const float c1x = 0.5f * a.ex, c1y = 0.5f * a.ey;                        // link 1: (0,0) -> elbow; half extents |c1|
-    const float c2x = fmaf(0.5f, a.gx, c1x), c2y = fmaf(0.5f, a.gy, c1y);    // link 2: elbow -> end effector
-    const float h2x = fabsf(c2x - a.ex), h2y = fabsf(c2y - a.ey);
+    const ArmBoxes b = make_arm_boxes(a);
     const int m = fl.m;
-    float acc = 1.0e30f;
+    float acc = 1.0e30f, m1, m2;
+    if (m == 3) {                            // scene_0's manual map (occupancy_grid.py:45-47): straight-line code
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            box_measures(b, fl.ctr[k], m1, m2);
+            acc = fminf(acc, fminf(m1, m2));
+        }
+    } else {
 #pragma unroll 1
-    for (int k = 0; k < m; ++k) {            // warp-uniform trip count; kept rolled so the hot loop stays compact
-        const float2 o = fl.ctr[k];
-        const float m1 = fmaxf(fabsf(c1x - o.x) - fabsf(c1x), fabsf(c1y - o.y) - fabsf(c1y));
-        const float m2 = fmaxf(fabsf(c2x - o.x) - h2x, fabsf(c2y - o.y) - h2y);
-        acc = fminf(acc, fminf(m1, m2));
+        for (int k = 0; k < m; ++k) {        // warp-uniform trip count; kept rolled so the hot loop stays compact
+            box_measures(b, fl.ctr[k], m1, m2);
+            acc = fminf(acc, fminf(m1, m2));
+        }
     }
     return acc;
 }
 
-// 0 / 1 certain, 2 undecided.  Warp-uniform loop over the (few) obstacles: range-overlap tests
-// for both links, then the narrow phase on the surviving (link, cell) pairs.
+// 0 / 1 certain, 2 undecided.  Warp-uniform loop over the (few) obstacles: the broad-phase measures pick
+// the (link, square) pairs, then the narrow phase runs on the surviving pairs.
 __device__ __forceinline__ int arm_fast_list(const FastList *fl, const ArmF &a, const FastConst &C) {
     const int m = fl->m;
-    const float x1lo = fminf(0.0f, a.ex), x1hi = fmaxf(0.0f, a.ex), y1lo = fminf(0.0f, a.ey), y1hi = fmaxf(0.0f, a.ey);
-    const float x2lo = fminf(a.ex, a.gx), x2hi = fmaxf(a.ex, a.gx), y2lo = fminf(a.ey, a.gy), y2hi = fmaxf(a.ey, a.gy);
+    const float hm = fl->hm;
+    const ArmBoxes bx = make_arm_boxes(a);
     uint32_t cand = 0;
 #pragma unroll 1
     for (int k = 0; k < m; ++k) {
-        const float4 q = fl->sq[k];
-        const bool o1 = (x1hi - q.x > -AG_M) && (q.z - x1lo > -AG_M) && (y1hi - q.y > -AG_M) && (q.w - y1lo > -AG_M);
-        const bool o2 = (x2hi - q.x > -AG_M) && (q.z - x2lo > -AG_M) && (y2hi - q.y > -AG_M) && (q.w - y2lo > -AG_M);
-        cand |= ((o1 ? 1u : 0u) | (o2 ? 2u : 0u)) << (2 * k);
+        float m1, m2;
+        box_measures(bx, fl->ctr[k], m1, m2);
+        cand |= ((m1 < hm ? 1u : 0u) | (m2 < hm ? 2u : 0u)) << (2 * k);
     }
     // narrow phase on the surviving (link, cell) pairs; the link is rebuilt per pair from `a`
     // (a dozen instructions) instead of keeping two LinkF live: registers matter more here
@@ -314,10 +337,60 @@ __device__ __forceinline__ int reach_fast(const FastConst &C, const ArmF &a) {
 
 // ---------------------------------------------------------------- cold path: the float64 reference arithmetic
 // Kept out of line so that the hot loop's register allocation is not dictated by it.
-AG_COLD int cold_exact_decide(const ag_params &P, const GridDev &G, const GridView &V, double q1,
-                                              double q2, int c, int r) {
+// Second-level filter, float64: the same division-free decision as narrow_f32 on the float64 arm, with
+// margins that only have to cover (a) our FK vs the reference's (CUDA sincos <= 2 ulp, glibc <= 1 ulp:
+// <= 4e-16 m) and (b) the reference's own rounding noise, which for |dx|,|dy| >= AG_MIN_DXY stays below
+// 1e-12 m (x1 = (-c - b*min_y)/a has absolute error ~ eps*|min_y*dx/dy|).  It settles the float32 filter's
+// undecided band (e.g. scene_0's link 1, whose 0.4 m reach is tangent to two squares) without the
+// reference's four divisions per pair; what it cannot settle goes to the EXACT engine.
+constexpr double AG_M64 = 1.0e-9;
+
+__device__ __forceinline__ int narrow_f64(double p0x, double p0y, double p1x, double p1y, double min_x, double min_y,
+                                          double max_x, double max_y, double side) {
+    const double dx = p1x - p0x, dy = p1y - p0y;
+    const double ecr = AG_M64 * (2.0 * (fabs(dx) + fabs(dy)) + 2.0 * side);
+    const double ux0 = min_x - p0x, ux1 = max_x - p0x, uy0 = min_y - p0y, uy1 = max_y - p0y;
+    const double a0 = ux0 * dy, a1 = ux1 * dy, b0 = uy0 * dx, b1 = uy1 * dx;
+    const double cmax = fmax(a0, a1) - fmin(b0, b1), cmin = fmin(a0, a1) - fmax(b0, b1);
+    if (!((cmax > -ecr) && (cmin < ecr))) return 0;                       // the line certainly misses the open square
+    if (fmin(fabs(dx), fabs(dy)) < (double)AG_MIN_DXY) return 2;
+    const double xlo = fmin(p0x, p1x), xhi = fmax(p0x, p1x), ylo = fmin(p0y, p1y), yhi = fmax(p0y, p1y);
+    const double a_min = fmin(fmin(xhi - min_x, max_x - xlo), fmin(yhi - min_y, max_y - ylo));
+    const double b_min = fmin(fmin(xlo - min_x, max_x - xhi), fmin(ylo - min_y, max_y - yhi));
+    if (!(a_min > -AG_M64) || b_min > AG_M64) return 0;                   // ranges certainly disjoint, or segment wholly inside
+    const bool p2_certain = (cmax > ecr) && (cmin < -ecr);
+    return (p2_certain && (a_min > AG_M64) && (b_min < -AG_M64)) ? 1 : 2;
+}
+
+// 0 / 1 certain, 2 undecided: both links against every square of the obstacle list, float64
+__device__ __forceinline__ int arm_f64_list(const GridDev &G, const FastList *fl, const Arm &A) {
+    int result = 0;
+    const int m = fl->m;
+#pragma unroll 1
+    for (int k = 0; k < 2 * m; ++k) {
+        const float4 qf = fl->sq[k >> 1];        // float32 copy of the corner: only used to skip far squares
+        const bool second = (k & 1) != 0;
+        const double p0x = second ? A.ex : 0.0, p0y = second ? A.ey : 0.0, p1x = second ? A.gx : A.ex, p1y = second ? A.gy : A.ey;
+        const double far = 1.0e-5;
+        if (fmax(p0x, p1x) < (double)qf.x - far || fmin(p0x, p1x) > (double)qf.z + far ||
+            fmax(p0y, p1y) < (double)qf.y - far || fmin(p0y, p1y) > (double)qf.w + far) continue;
+        const int cell = fl->cell[k >> 1];       // (row << 16) | col of the square: exact float64 corners
+        const double mnx = fl->vmin_x[cell & 0xFFFF], mny = fl->vmin_y[cell >> 16];
+        const int v = narrow_f64(p0x, p0y, p1x, p1y, mnx, mny, __dadd_rn(mnx, G.side), __dadd_rn(mny, G.side), G.side);
+        if (v == 1) return 1;
+        result |= v;
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------- cold path: float64
+// Kept out of line so that the hot loop's register allocation is not dictated by it.
+// c / r: the float32 filter's verdicts (0, 1, or 2 = undecided).
+AG_COLD int cold_exact_decide(const ag_params &P, const GridDev &G, const GridView &V, const FastList *fl, double q1,
+                              double q2, int c, int r) {
     const Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
     int fh = 0, axis = 0;
+    if (c == 2 && fl != nullptr && fl->m >= 0) c = arm_f64_list(G, fl, A);
     const bool hit = (c == 2) ? arm_collides<AG_ENGINE_EXACT, false>(G, V, A, P.section_eps, fh, axis) : (c == 1);
     const bool reached = (r == 2) ? target_reached_cart(P, A) : (r == 1);
     return (hit ? 1 : 0) | (reached ? 2 : 0) | (axis << 2);
@@ -350,7 +423,7 @@ __device__ __forceinline__ int fast_decide(const ag_params &P, const GridDev &G,
         if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
         else r = ok ? reach_fast(C, a) : 2;
     }
-    if (c == 2 || r == 2) return cold_exact_decide(P, G, V, q1, q2, c, r);
+    if (c == 2 || r == 2) return cold_exact_decide(P, G, V, fl, q1, q2, c, r);
     return c | (r << 1);
 }
 

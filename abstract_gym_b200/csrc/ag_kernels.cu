@@ -299,7 +299,8 @@ struct HotCtx {
     float rw;
     uint32_t flags, mask;
     int el_off;              // episode length after step t = el_off + t + 1
-    int t, d, undecided;
+    int t, d;
+    int undecided;           // 0, or 16 | c | r << 2: the float32 filter's verdicts (2 = undecided) of step t
 };
 
 // one step record (experiment_0.py:23-25): joint_1, joint_2, step_reward, flags, post-step / pre-reset
@@ -326,7 +327,7 @@ __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, 
     B.V.bits = hc->vbits; B.V.min_x = hc->vminx; B.V.min_y = hc->vminy; B.fl = hc->fl;
     if (hc->undecided) {
         atomicAdd(&s_acc[AG_ST_COUNT + AG_DIAG_EXACT_STEPS], 1ull);
-        d = cold_exact_decide(P, G, B.V, q1, q2, 2, P.choose_j_tar ? (target_reached_joint(P, q1, q2) ? 1 : 0) : 2);
+        d = cold_exact_decide(P, G, B.V, B.fl, q1, q2, hc->undecided & 3, (hc->undecided >> 2) & 3);   // the filter's verdicts
         if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
         if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
         store_record<RECORD>(A, hc->o, q1, q2, rw, fl);                           // experiment_0.py:23-25
@@ -399,7 +400,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
             const float2 *act = hc.act;
             float2 a_next = hc.a_next;
             int64_t o = hc.o;
-            int t = hc.t, d = 0;
+            int t = hc.t, d = 0, cr = 0;
             bool undecided = false, event = false;
             // a lane whose sticky state is not clean (flags / reward left by earlier step() calls) is
             // forced through the slow branch: an infinite threshold makes its reach pre-test fire
@@ -429,7 +430,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                         const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
                         const float sep = broad_list(s_fl, a);
                         const float worst = fmaxf(fabsf(C.tx - a.gx), fabsf(C.ty - a.gy));
-                        slow = !(sep >= s_fl.hm) | !(worst >= reach_thr) | !ok | (s_fl.m < 0);   // NaN-safe: NaN is slow
+                        slow = !(sep >= s_fl.hm) | !(worst >= reach_thr) | !ok;             // NaN-safe: NaN is slow
                         if (P.choose_j_tar) slow |= target_reached_joint(P, q1, q2);
                         store_record<RECORD>(A, o, q1, q2, 0.0f, 0u);            // an uneventful step; slow lanes rewrite theirs
                     }
@@ -446,11 +447,12 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                         if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
                         else r = ok ? reach_fast(C, a) : 2;
                         undecided = ((c | r) & 2) != 0;
+                        cr = c | (r << 2);
                         d = (c & 1) | ((r & 1) << 1);
                     } else if constexpr (ENGINE == AG_ENGINE_FAST) {
-                        d = fast_filter<BP>(P, G, B.V, B.fl, C, q1, q2);         // (c | r << 2), c,r in {0,1,2}
-                        undecided = ((d | (d >> 2)) & 2) != 0;
-                        d = (d & 1) | ((d >> 1) & 2);                            // -> bit0 collision, bit1 reached
+                        cr = fast_filter<BP>(P, G, B.V, B.fl, C, q1, q2);        // (c | r << 2), c,r in {0,1,2}
+                        undecided = ((cr | (cr >> 2)) & 2) != 0;
+                        d = (cr & 1) | ((cr >> 1) & 2);                          // -> bit0 collision, bit1 reached
                     } else {
                         d = step_decide<ENGINE, BP>(P, G, B, C, q1, q2);
                     }
@@ -469,7 +471,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
             // registers -> struct
             hc.q1 = q1; hc.q2 = q2; hc.rw = rw; hc.flags = fl;
             if (t >= A.K) break;
-            hc.act = act; hc.a_next = a_next; hc.o = o; hc.t = t; hc.d = d; hc.undecided = undecided ? 1 : 0;
+            hc.act = act; hc.a_next = a_next; hc.o = o; hc.t = t; hc.d = d; hc.undecided = undecided ? (cr | 16) : 0;
             if (event) {
                 atomicAdd(&s_acc[AG_ST_COUNT + AG_DIAG_COLD_CALLS], 1ull);
                 cold_section<ENGINE, BP, HAS_RESET_U, RECORD>(P, G, A, &hc, s_acc);
