@@ -75,29 +75,55 @@ __device__ __forceinline__ void sincos_half(float f, float &s, float &c) {
     c = fmaf(pc, u, 0.9999999403953552f);
 }
 
-// float32 (sin, cos) * len of a float64 angle.  The reduction to half turns (j/pi, round to nearest
-// integer k, remainder f) stays in float64 (3 DP ops); sin(j) = (-1)^k sin(pi f), cos(j) = (-1)^k cos(pi f),
-// and the sign is folded into the link length with one XOR, so there is no select on the ALU pipe.
-__device__ __forceinline__ void sincos_len_f32_of_f64(double j, float len, float &s_len, float &c_len) {
+// Packed float32x2 arithmetic (Blackwell FFMA2 / FMUL2: two float32 operations per issue slot); the
+// two halves carry the two joint angles through the same polynomial.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)),
+        "l"(*reinterpret_cast<unsigned long long *>(&b)), "l"(*reinterpret_cast<unsigned long long *>(&c)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long *>(&a)),
+        "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// half-turn remainder f (float32) and signed length of one float64 angle: j = pi*(k + f), |f| <= 0.5;
+// sin(j) = (-1)^k sin(pi f), cos(j) = (-1)^k cos(pi f): the sign is folded into the link length with one
+// XOR, so there is no select on the ALU pipe.  The reduction stays in float64 (3 DP ops).
+__device__ __forceinline__ void reduce_half_turns(double j, float len, float &f, float &sl) {
     const double t = j * 0.31830988618379067154;               // half turns
     const double tk = t + 6755399441055744.0;                  // 1.5*2^52: rounds to nearest integer
     const uint32_t k = (uint32_t)__double2loint(tk);
-    const float f = (float)(t - (tk - 6755399441055744.0));
-    float sq, cq;
-    sincos_half(f, sq, cq);
-    const float sl = __uint_as_float(__float_as_uint(len) ^ (k << 31));
-    s_len = sq * sl; c_len = cq * sl;
+    f = (float)(t - (tk - 6755399441055744.0));
+    sl = __uint_as_float(__float_as_uint(len) ^ (k << 31));
 }
 
 // ok=false when an angle is outside the range where the reduction above is trustworthy (also NaN)
 __device__ __forceinline__ ArmF fast_forward_kinematics(double j1, double j2, const FastConst &C, bool &ok) {
-    float s1, c1, s2, c2;
-    sincos_len_f32_of_f64(j1, C.l1, s1, c1);
-    sincos_len_f32_of_f64(j2, C.l2, s2, c2);
+    float2 f, sl;
+    reduce_half_turns(j1, C.l1, f.x, sl.x);
+    reduce_half_turns(j2, C.l2, f.y, sl.y);
     ok = (fabs(j1) < 1048576.0) && (fabs(j2) < 1048576.0);     // two DSETP on the (idle) FP64 pipe
+    // sincos_half() on both angles at once: same coefficients, same operation order, FFMA2
+    const float2 u = mul2(f, f);
+    float2 ps = splat2(0.07765940576791763f);
+    ps = fma2(ps, u, splat2(-0.5982921719551086f));
+    ps = fma2(ps, u, splat2(2.5500776767730713f));
+    ps = fma2(ps, u, splat2(-5.167710304260254f));
+    ps = fma2(ps, u, splat2(3.1415927410125732f));
+    float2 pc = splat2(0.2196967899799347f);
+    pc = fma2(pc, u, splat2(-1.3318802118301392f));
+    pc = fma2(pc, u, splat2(4.058412075042725f));
+    pc = fma2(pc, u, splat2(-4.934792995452881f));
+    pc = fma2(pc, u, splat2(0.9999999403953552f));
+    const float2 s = mul2(mul2(ps, f), sl), c = mul2(pc, sl);  // (sin j1 * l1, sin j2 * l2), (cos j1 * l1, cos j2 * l2)
     ArmF a;
-    a.ex = c1; a.ey = s1;
-    a.gx = c2 + a.ex; a.gy = s2 + a.ey;
+    a.ex = c.x; a.ey = s.x;
+    a.gx = c.y + a.ex; a.gy = s.y + a.ey;
     return a;
 }
 

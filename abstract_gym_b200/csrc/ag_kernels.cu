@@ -289,19 +289,31 @@ __device__ __forceinline__ int step_decide(const ag_params &P, const GridDev &G,
 // 64-register budget (DESIGN.md "register allocation of K4").
 struct HotCtx {
     double q1, q2;
-    const float2 *act;       // action of step t+1 (prefetched into a_next)
+    const float2 *act;       // action row of step t + AG_RING - 1: the next one to prefetch
     const uint32_t *vbits;   // this thread's grid view
     const double *vminx, *vminy;
     const FastList *fl;
     int64_t o;               // record offset of step t
     int64_t e;               // env index within the launch
-    float2 a_next;
     float rw;
     uint32_t flags, mask;
     int el_off;              // episode length after step t = el_off + t + 1
     int t, d;
     int undecided;           // 0, or 16 | c | r << 2: the float32 filter's verdicts (2 = undecided) of step t
 };
+
+// Action prefetch ring: every thread streams its own actions global -> shared with cp.async (LDGSTS), AG_RING - 1
+// steps ahead of their use, so that no register and no warp ever waits for a DRAM round trip (with a
+// register prefetch one step ahead, 37 % of all stall samples were long-scoreboard waits on that load:
+// profiles/r1g).  Slot (t mod AG_RING) of row threadIdx.x holds the action of step t.
+constexpr int AG_RING = 4;
+
+__device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // one step record (experiment_0.py:23-25): joint_1, joint_2, step_reward, flags, post-step / pre-reset
 template <bool RECORD>
@@ -374,6 +386,8 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ FastList s_fl;
     __shared__ unsigned long long s_acc[AG_ST_COUNT + AG_DIAG_COUNT];
+    __shared__ __align__(16) float2 s_ring[HAS_ACT ? AG_RING * BLOCK : 1];
+    __shared__ __align__(16) float4 s_arm[(ENGINE == AG_ENGINE_FAST && BP == BP_LIST) ? BLOCK : 1];   // float32 arm of a slow lane
     if (threadIdx.x < AG_ST_COUNT + AG_DIAG_COUNT) s_acc[threadIdx.x] = 0;
     const BlockCtx B0 = block_prologue<ENGINE>(G, A.env_id0, A.n, smem, &s_fl);
     __syncthreads();
@@ -383,9 +397,18 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
         HotCtx hc;
         hc.q1 = A.j1[e0]; hc.q2 = A.j2[e0]; hc.rw = A.reward[e0]; hc.flags = A.flags[e0];
         hc.el_off = (int)A.ep_len[e0];
-        hc.act = HAS_ACT ? reinterpret_cast<const float2 *>(A.actions) + e0 : nullptr;
-        hc.a_next = make_float2(0.f, 0.f);
-        if (HAS_ACT) hc.a_next = __ldcs(hc.act);                                 // streamed once
+        hc.act = nullptr;
+        const uint32_t ring0 = smem_u32(&s_ring[HAS_ACT ? threadIdx.x : 0]);     // this thread's column of the ring
+        if (HAS_ACT) {                                                           // steps 0 .. AG_RING-2 in flight
+            const float2 *p = reinterpret_cast<const float2 *>(A.actions) + e0;
+#pragma unroll
+            for (int i = 0; i < AG_RING - 1; ++i) {
+                if (i < A.K) cp_async8(ring0 + (uint32_t)i * (BLOCK * 8), p);
+                cp_async_commit();
+                p += A.row_stride;
+            }
+            hc.act = p;
+        }
         hc.vbits = B0.V.bits; hc.vminx = B0.V.min_x; hc.vminy = B0.V.min_y; hc.fl = B0.fl;
         hc.o = e0; hc.e = e0; hc.mask = __activemask(); hc.t = 0; hc.d = 0; hc.undecided = 0;
         const uint32_t sc0 = A.step_ctr[e0];
@@ -398,7 +421,6 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
             uint32_t fl = hc.flags;
             const uint32_t warp_mask = FULL ? 0xFFFFFFFFu : hc.mask;   // FULL: n % 32 == 0, every warp is complete
             const float2 *act = hc.act;
-            float2 a_next = hc.a_next;
             int64_t o = hc.o;
             int t = hc.t, d = 0, cr = 0;
             bool undecided = false, event = false;
@@ -414,9 +436,12 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                 for (; t < A.K; ++t, o += A.row_stride) {                        // ---- inner
                     double d1, d2;
                     if (HAS_ACT) {
-                        const float2 an = a_next;
+                        if (t + (AG_RING - 1) < A.K)                             // refill the slot consumed last step
+                            cp_async8(ring0 + ((uint32_t)(t + AG_RING - 1) & (AG_RING - 1)) * (BLOCK * 8), act);
+                        cp_async_commit();
                         act += A.row_stride;
-                        if (t + 1 < A.K) a_next = __ldcs(act);                   // prefetch the next step's action
+                        cp_async_wait<AG_RING - 1>();                            // this step's action has landed
+                        const float2 an = s_ring[((uint32_t)t & (AG_RING - 1)) * BLOCK + threadIdx.x];
                         d1 = (double)an.x; d2 = (double)an.y;
                     } else {
                         double u0, u1;
@@ -432,6 +457,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                         const float worst = fmaxf(fabsf(C.tx - a.gx), fabsf(C.ty - a.gy));
                         slow = !(sep >= s_fl.hm) | !(worst >= reach_thr) | !ok;             // NaN-safe: NaN is slow
                         if (P.choose_j_tar) slow |= target_reached_joint(P, q1, q2);
+                        if (slow) s_arm[threadIdx.x] = make_float4(a.ex, a.ey, ok ? a.gx : __int_as_float(0x7fc00000), a.gy);
                         store_record<RECORD>(A, o, q1, q2, 0.0f, 0u);            // an uneventful step; slow lanes rewrite theirs
                     }
                     if (__any_sync(warp_mask, slow)) break;
@@ -440,8 +466,10 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                 event = false;
                 if (slow) {
                     if constexpr (LIST) {
-                        bool ok;                                                 // recomputed (identical values): cheaper than
-                        const ArmF a = fast_forward_kinematics(q1, q2, C, ok);   // keeping the arm live out of the inner loop
+                        const float4 af = s_arm[threadIdx.x];                    // stashed by this lane in the inner loop
+                        ArmF a;                                                  // (keeping it in registers costs spills there)
+                        a.ex = af.x; a.ey = af.y; a.gx = af.z; a.gy = af.w;
+                        const bool ok = (af.z == af.z);                          // NaN marks angles outside the filter's range
                         const int c = (ok && s_fl.m >= 0) ? arm_fast_list(&s_fl, a, C) : 2;
                         int r;
                         if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
@@ -460,7 +488,8 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                     if (!undecided) {
                         if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
                         if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
-                        store_record<RECORD>(A, o, q1, q2, rw, fl);                                // experiment_0.py:23-25
+                        if (!LIST || fl != 0 || rw != 0.0f)                                        // else: already recorded
+                            store_record<RECORD>(A, o, q1, q2, rw, fl);                            // experiment_0.py:23-25
                         event = (fl | (d >> 2)) != 0;
                         reach_thr = (rw != 0.0f) ? __int_as_float(0x7f800000) : reach_thr_clean;
                     }
@@ -471,7 +500,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
             // registers -> struct
             hc.q1 = q1; hc.q2 = q2; hc.rw = rw; hc.flags = fl;
             if (t >= A.K) break;
-            hc.act = act; hc.a_next = a_next; hc.o = o; hc.t = t; hc.d = d; hc.undecided = undecided ? (cr | 16) : 0;
+            hc.act = act; hc.o = o; hc.t = t; hc.d = d; hc.undecided = undecided ? (cr | 16) : 0;
             if (event) {
                 atomicAdd(&s_acc[AG_ST_COUNT + AG_DIAG_COLD_CALLS], 1ull);
                 cold_section<ENGINE, BP, HAS_RESET_U, RECORD>(P, G, A, &hc, s_acc);
