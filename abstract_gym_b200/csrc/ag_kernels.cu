@@ -61,11 +61,19 @@ __device__ __forceinline__ BlockCtx block_prologue(const GridDev &G, int64_t env
     return B;
 }
 
-// block statistics: shared-memory atomics at (rare) events, one global atomic per slot per block
+// Block statistics: shared-memory atomics at (rare) events, one global atomic per slot per block.
+// 64-bit shared atomics compile to compare-and-swap spin loops (ATOMS.CAST.SPIN), so every slot but the
+// episode-length sum is accumulated as a native 32-bit add on the low word of its 64-bit cell: a block adds at
+// most blockDim * K (K <= AG_MAX_K) per slot and launch, which cannot carry.  The return slot is signed.
+constexpr int AG_MAX_K = 65536;
+__device__ __forceinline__ void acc32(unsigned long long *s_acc, int slot, int v) {
+    atomicAdd(reinterpret_cast<unsigned int *>(&s_acc[slot]), (unsigned int)v);
+}
 __device__ __forceinline__ void stats_flush(unsigned long long *s_acc, unsigned long long *gstats) {
     __syncthreads();
     if (threadIdx.x < AG_ST_COUNT && gstats != nullptr) {
-        const unsigned long long v = s_acc[threadIdx.x];
+        unsigned long long v = s_acc[threadIdx.x];
+        if (threadIdx.x == AG_ST_RETURN_MILLI) v = (unsigned long long)(long long)(int)(unsigned int)v;   // sign-extend
         if (v != 0) atomicAdd(&gstats[threadIdx.x], v);
     }
 }
@@ -197,8 +205,8 @@ __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const Grid
             reinterpret_cast<double2 *>(dist)[e] =
                 make_double2(fabs(__dsub_rn(P.target_x, A.gx)), fabs(__dsub_rn(P.target_y, A.gy)));
         if (WANT_FIRST) first_hit[e] = h ? fh : -1;
-        atomicAdd(&s_acc[AG_ST_ENV_STEPS], 1ull);
-        if (axis) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)axis);
+        acc32(s_acc, AG_ST_ENV_STEPS, 1);
+        if (axis) acc32(s_acc, AG_ST_AXIS_ALIGNED, axis);
     }
     stats_flush(s_acc, stats);
 }
@@ -213,7 +221,7 @@ __device__ __forceinline__ void resample_pose(const ag_params &P, const GridDev 
     int tries = 0;
     while (colliding) {
         if (tries >= P.max_reset_tries || (HAS_RESET_U && rc >= (uint32_t)R)) {
-            atomicAdd(&s_acc[AG_ST_STUCK_RESETS], 1ull);
+            acc32(s_acc, AG_ST_STUCK_RESETS, 1);
             break;
         }
         double u0, u1;
@@ -228,7 +236,7 @@ __device__ __forceinline__ void resample_pose(const ag_params &P, const GridDev 
         j2 = __dmul_rn(__dmul_rn(u1, 3.141592653589793), 2.0);    // :181
         int fh = 0, axis = 0;
         colliding = pose_collides<ENGINE, false, BP, COLD>(P, G, B, C, j1, j2, fh, axis);
-        if (axis) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)axis);
+        if (axis) acc32(s_acc, AG_ST_AXIS_ALIGNED, axis);
     }
 }
 
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(AG_BLOCK) k_reset(const ag_params P, const Gri
         uint32_t rc = reset_ctr[e];
         int fh = 0, axis = 0;
         const bool h = pose_collides<ENGINE, false>(P, G, B, C, q1, q2, fh, axis);
-        if (axis) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)axis);
+        if (axis) acc32(s_acc, AG_ST_AXIS_ALIGNED, axis);
         resample_pose<ENGINE, HAS_RESET_U>(P, G, B, C, h, q1, q2, rc, HAS_RESET_U ? reset_u + (int64_t)e * R * 2 : nullptr,
                                            R, seed, (uint64_t)(env_id0 + e), s_acc);
         j1[e] = q1; j2[e] = q2; reset_ctr[e] = rc;
@@ -329,8 +337,8 @@ __device__ __forceinline__ void store_record(const RolloutDev &A, int64_t o, dou
 // Cold section, out of line: (1) finish a step whose float32 filter was undecided with the
 // float64 reference arithmetic, (2) episode end (experiment_0.py:30-34): statistics + Scene.reset().
 template <int ENGINE, int BP, bool HAS_RESET_U, bool RECORD>
-__device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, const RolloutDev &A, HotCtx *hc,
-                                          unsigned long long *s_acc) {
+__device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, const FastConst &C, const RolloutDev &A,
+                                          HotCtx *hc, unsigned long long *s_acc) {
     double q1 = hc->q1, q2 = hc->q2;
     float rw = hc->rw;
     uint32_t fl = hc->flags;
@@ -338,22 +346,21 @@ __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, 
     BlockCtx B;
     B.V.bits = hc->vbits; B.V.min_x = hc->vminx; B.V.min_y = hc->vminy; B.fl = hc->fl;
     if (hc->undecided) {
-        atomicAdd(&s_acc[AG_ST_COUNT + AG_DIAG_EXACT_STEPS], 1ull);
+        acc32(s_acc, AG_ST_COUNT + AG_DIAG_EXACT_STEPS, 1);
         d = cold_exact_decide(P, G, B.V, B.fl, q1, q2, hc->undecided & 3, (hc->undecided >> 2) & 3);   // the filter's verdicts
         if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
         if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
         store_record<RECORD>(A, hc->o, q1, q2, rw, fl);                           // experiment_0.py:23-25
     }
-    if (d >> 2) atomicAdd(&s_acc[AG_ST_AXIS_ALIGNED], (unsigned long long)(d >> 2));
+    if (d >> 2) acc32(s_acc, AG_ST_AXIS_ALIGNED, d >> 2);
     if (fl) {                                                                     // experiment_0.py:30-34
-        atomicAdd(&s_acc[AG_ST_EPISODES], 1ull);
-        if (fl & AG_FLAG_COLLISION) atomicAdd(&s_acc[AG_ST_COLLISIONS], 1ull);
-        if (fl & AG_FLAG_DONE) atomicAdd(&s_acc[AG_ST_SUCCESSES], 1ull);
+        acc32(s_acc, AG_ST_EPISODES, 1);
+        if (fl & AG_FLAG_COLLISION) acc32(s_acc, AG_ST_COLLISIONS, 1);
+        if (fl & AG_FLAG_DONE) acc32(s_acc, AG_ST_SUCCESSES, 1);
         atomicAdd(&s_acc[AG_ST_EP_LEN_SUM], (unsigned long long)(uint32_t)(hc->el_off + hc->t + 1));
-        atomicAdd(&s_acc[AG_ST_RETURN_MILLI], (unsigned long long)(long long)llrintf(rw * 1e-3f));
+        acc32(s_acc, AG_ST_RETURN_MILLI, __float2int_rn(rw * 1e-3f));
         if (d & 1) {   // Scene.reset(): the pose is unchanged since the step, so collision_check() == (d & 1)
             const int64_t e = hc->e;
-            const FastConst C = make_fast_const(P, G);
             uint32_t rc = A.reset_ctr[e];
             resample_pose<ENGINE, HAS_RESET_U, BP, false>(P, G, B, C, true, q1, q2, rc,
                                                           HAS_RESET_U ? A.reset_u + e * A.R * 2 : nullptr, A.R, A.seed,
@@ -502,12 +509,12 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
             if (t >= A.K) break;
             hc.act = act; hc.o = o; hc.t = t; hc.d = d; hc.undecided = undecided ? (cr | 16) : 0;
             if (event) {
-                atomicAdd(&s_acc[AG_ST_COUNT + AG_DIAG_COLD_CALLS], 1ull);
-                cold_section<ENGINE, BP, HAS_RESET_U, RECORD>(P, G, A, &hc, s_acc);
+                acc32(s_acc, AG_ST_COUNT + AG_DIAG_COLD_CALLS, 1);
+                cold_section<ENGINE, BP, HAS_RESET_U, RECORD>(P, G, C, A, &hc, s_acc);
             } else { hc.t = t + 1; hc.o = o + A.row_stride; }
-            if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[AG_ST_COUNT + AG_DIAG_WARP_EXITS], 1ull);
+            if ((threadIdx.x & 31) == 0) acc32(s_acc, AG_ST_COUNT + AG_DIAG_WARP_EXITS, 1);
         }
-        atomicAdd(&s_acc[AG_ST_ENV_STEPS], (unsigned long long)A.K);
+        acc32(s_acc, AG_ST_ENV_STEPS, A.K);
         A.j1[e0] = hc.q1; A.j2[e0] = hc.q2; A.reward[e0] = hc.rw; A.flags[e0] = (uint8_t)hc.flags;
         A.ep_len[e0] = (uint32_t)(hc.el_off + A.K);
     }
@@ -625,7 +632,7 @@ ag_status launch_rollout_e(const ag_params &P, const GridDev &G, const RolloutDe
 ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, int64_t row_stride,
                           void *stream) {
     if (!p || !g || !a) return AG_ERR_NULL;
-    if (a->n < 0 || a->K < 1) return AG_ERR_SHAPE;
+    if (a->n < 0 || a->K < 1 || a->K > AG_MAX_K) return AG_ERR_SHAPE;
     if (a->n == 0) return AG_OK;
     if (!a->j1 || !a->j2 || !a->reward || !a->flags || !a->step_ctr || !a->reset_ctr || !a->ep_len || !a->stats)
         return AG_ERR_NULL;

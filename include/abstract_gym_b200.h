@@ -177,7 +177,7 @@ AG_API ag_status ag_reset(const ag_params *p, const ag_grid *g, double *j1, doub
 typedef struct ag_rollout_args {
     int64_t n;
     int64_t env_id0;
-    int32_t K;
+    int32_t K;               /* steps fused in this launch, 1 .. 65536 */
     int32_t engine;
     uint64_t seed;
     const float *actions;
