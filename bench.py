@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--rollout-steps", type=int, default=64, help="env-steps fused per launch (K)")
     ap.add_argument("--engine", default="fast", choices=["fast", "exact"])
     ap.add_argument("--mode", default="record", choices=["record", "stats"])
+    ap.add_argument("--grid", default="scene0", choices=["scene0", "c4", "c5"],
+                    help="scene0: manual 9x9 map (BASELINE configs[2], the default bench line); c4: one 1024x1024 "
+                         "Bernoulli(0.002) map (configs[3]); c5: a distinct 256x256 Bernoulli(0.008) map per 256 envs (configs[4])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-envs", type=int, default=1 << 17)
@@ -119,17 +122,16 @@ def run_reference(args, rank, world):
     import numpy as np
     from oracle import oracle as orc
     K = args.rollout_steps
-    n = args.cpu_sample_envs
     rng = np.random.default_rng(0)
-    sq = orc.manual_grid()[0]
+    sqs, epg, n = oracle_workload(args, orc, np)
     st = orc.RolloutState(rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n))
     actions = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32) if args.mode == "record" else None
     cores = host_cores()                             # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
     for _ in range(args.warmup):
-        orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
+        orc.rollout(st, K, sqs, envs_per_grid=epg, seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
+        orc.rollout(st, K, sqs, envs_per_grid=epg, seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
     dt = time.perf_counter() - t0
     value = n * K * args.steps / dt
     sample = "%d envs x %d env-steps per step (1/%d of one GPU's batch), OpenMP over envs" % (n, K, max(1, args.envs // n))
@@ -145,6 +147,19 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def oracle_workload(args, orc, np):
+    """(squares per grid, envs_per_grid, sample envs) of the CPU arms for --grid.  The oracle tests every obstacle
+    (the reference's O(#obstacles) loop), so the high-resolution maps get a smaller sample."""
+    if args.grid == "scene0":
+        return [orc.manual_grid()[0]], None, args.cpu_sample_envs
+    if args.grid == "c4":
+        occ = (np.random.default_rng(4).random((1024, 1024)) < 0.002).astype(np.uint8)
+        return [orc.grid_squares(occ)[0]], None, min(args.cpu_sample_envs, 1 << 11)
+    rng = np.random.default_rng(5)
+    occs = [(rng.random((256, 256)) < 0.008).astype(np.uint8) for _ in range(8)]
+    return [orc.grid_squares(o)[0] for o in occs], 256, min(args.cpu_sample_envs, 1 << 11)
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -152,11 +167,17 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+GRID_NAMES = {"scene0": "scene_0 manual 9x9 grid (3 obstacles)",
+              "c4": "one 1024x1024 bit-packed grid, Bernoulli(0.002) obstacles (128 KiB, L2-resident)",
+              "c5": "a distinct 256x256 Bernoulli(0.008) grid per batch of 256 envs (8 KiB each, staged by TMA)"}
+
+
 def workload_config(args, world):
-    return {"workload": "scene_0 manual 9x9 grid (3 obstacles), %d envs/GPU, fused %d-step rollout (K4), %s mode, "
-                        "random actions (u-0.5)*0.1, auto-reset" % (args.envs, args.rollout_steps, args.mode.upper()),
+    return {"workload": "%s, %d envs/GPU, fused %d-step rollout (K4), %s mode, "
+                        "random actions (u-0.5)*0.1, auto-reset" % (GRID_NAMES[args.grid], args.envs, args.rollout_steps,
+                                                                    args.mode.upper()),
             "envs_per_gpu": args.envs, "rollout_steps": args.rollout_steps, "mode": args.mode, "engine": args.engine,
-            "grid": "9x9 manual", "parallelism": "env-sharded x%d, replicated grid, stats all-reduce" % world,
+            "grid": args.grid, "parallelism": "env-sharded x%d, replicated grid, stats all-reduce" % world,
             "l2_policy": "inputs_exceed_l2 (%.0f MB streamed per launch)" %
                          (args.envs * args.rollout_steps * (21 if args.mode == "record" else 0) / 1e6)}
 
@@ -164,16 +185,17 @@ def workload_config(args, world):
 def cpu_baseline(args):
     import numpy as np
     from oracle import oracle as orc
-    K, n = args.rollout_steps, args.cpu_sample_envs * 2
+    K = args.rollout_steps
     rng = np.random.default_rng(0)
-    sq = orc.manual_grid()[0]
+    sqs, epg, n = oracle_workload(args, orc, np)
+    n *= 2
     st = orc.RolloutState(rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n))
     actions = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32) if args.mode == "record" else None
     cores = host_cores()
-    orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
+    orc.rollout(st, K, sqs, envs_per_grid=epg, seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
     reps, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < 10.0:
-        orc.rollout(st, K, [sq], seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
+        orc.rollout(st, K, sqs, envs_per_grid=epg, seed=0, actions_f32=actions, record=args.mode == "record", threads=cores)
         reps += 1
     dt = time.perf_counter() - t0
     return {"value": n * K * reps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
@@ -192,7 +214,14 @@ def run_ours(args, rank, world, local):
     record = args.mode == "record"
     lo = rank * n                                    # weak scaling: every rank owns n envs, global ids [lo, lo+n)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    grid = ag.OccupancyGrid(size=9, random_obstacle=False)
+    if args.grid == "scene0":
+        grid = ag.OccupancyGrid(size=9, random_obstacle=False)
+    elif args.grid == "c4":
+        grid = ag.OccupancyGrid(size=9, random_obstacle=False)
+        grid.load_from_matrix((np.random.default_rng(4).random((1024, 1024)) < 0.002).astype(np.uint8))
+    else:
+        ggen = torch.Generator(device=dev).manual_seed(5)     # same maps on every rank; envs pick them by global id
+        grid = ag.BatchedOccupancyGrid.random(max(1, world * n // 256), 256, 0.008, 256, device=dev, generator=ggen)
     robot = ag.BatchedTwoJointRobot.random(n, device=dev, generator=gen)
     scene = ag.BatchedScene(robot, grid, engine=args.engine, seed=0, env_id0=lo)
     scene.random_valid_pose()                        # experiment_0.py:16
