@@ -407,3 +407,50 @@ def test_fast_fk_error_budget(ag, torch_):
     rb = ag.BatchedTwoJointRobot((u[0] - 0.5) * 2000.0, (u[1] - 0.5) * 2000.0)     # |j| up to 1000 rad
     sc = ag.BatchedScene(rb, g)
     assert int((sc.collision_check(engine="exact") != sc.collision_check(engine="fast")).sum().item()) == 0
+
+
+# ------------------------------------------------------------------ the reference's data product
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,seed", [("dense9_seed3", 3), ("dense9_seed4", 4)])
+def test_dropin_loop_reproduces_reference_data_list(ag, golden_dir, tmp_path, name, seed):
+    """experiment_0.py:11-37,54-57 with the drop-in classes, seeded like oracle/make_golden_datalist.py:
+    the exported data_list.txt equals the file the UNMODIFIED reference wrote, byte for byte."""
+    from abstract_gym_b200.experiment.experiment_0 import Trajectories
+    occ_m = np.load(os.path.join(golden_dir, "data_list_dense9_occ.npy"))
+    np.random.seed(seed)
+    rob = ag.TwoJointRobot(joint_1=1.0, joint_2=2.5)
+    occ = ag.OccupancyGrid(size=9, random_obstacle=False, obstacle_probability=0.01)
+    occ.load_from_matrix(occ_m)
+    s = ag.Scene(robot=rob, env=occ, visualize=False)
+    s.random_valid_pose()
+    rows = []
+    for i in range(400):
+        action = s.sample_action(scale_factor=0.1)
+        j1, j2, step_reward, done, collision = s.step(action)
+        rows.append([j1, j2, action[0], action[1], step_reward, (1 if collision else 0) | (2 if done else 0)])
+        if done or collision:
+            s.reset()
+    a = np.array(rows, dtype=np.float64)
+    col = lambda i: a[:, i:i + 1].copy()
+    tr = Trajectories(col(0), col(1), col(2), col(3), col(4), a[:, 5:6].astype(np.uint8))
+    out = tmp_path / "data_list.txt"
+    tr.export_text(str(out), numpy2=True)
+    assert out.read_bytes() == open(os.path.join(golden_dir, "data_list_%s.txt" % name), "rb").read()
+
+
+@pytest.mark.gpu
+def test_experiment_drivers_fast_equals_exact(ag, torch_):
+    """run_experiment (fused rollout, float32 records) and run_experiment_exact (step + masked reset, float64)
+    produce the same episodes on the same actions and reset candidates"""
+    from abstract_gym_b200.experiment.experiment_0 import run_experiment, run_experiment_exact
+    n, K, R = 3000, 40, 24
+    rng = np.random.default_rng(21)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    fast = run_experiment(make_scene(ag, torch_, g, j1, j2, seed=6), K, chunk_steps=16, actions=acts)
+    exact = run_experiment_exact(make_scene(ag, torch_, g, j1, j2, seed=6), K, actions=acts.astype(np.float64))
+    assert np.array_equal(fast.flags, exact.flags) and np.array_equal(fast.reward, exact.reward)
+    assert np.array_equal(fast.j1, exact.j1.astype(np.float32)) and np.array_equal(fast.j2, exact.j2.astype(np.float32))
+    assert fast.episode_index().tolist() == exact.episode_index().tolist() and len(fast.episode_index()) > 20
