@@ -15,7 +15,10 @@ from .utils.collision_checker import CollisionChecker, segment_square_arrays
 from .robot.two_joint_robot import TwoJointRobot, BatchedTwoJointRobot, forward_kinematics
 from .environment.occupancy_grid import OccupancyGrid, BatchedOccupancyGrid, DeviceGrid
 from .scenario.scene_0 import Scene, BatchedScene
+from .scenario.vector_env import VectorEnv
+from .experiment.experiment_0 import Trajectories, run_experiment, run_experiment_exact
 
 __all__ = ["AgError", "ENGINES", "STAT_NAMES", "default_params", "launch_count", "Point", "Line", "Square",
            "CollisionChecker", "segment_square_arrays", "TwoJointRobot", "BatchedTwoJointRobot",
-           "forward_kinematics", "OccupancyGrid", "BatchedOccupancyGrid", "DeviceGrid", "Scene", "BatchedScene"]
+           "forward_kinematics", "OccupancyGrid", "BatchedOccupancyGrid", "DeviceGrid", "Scene", "BatchedScene", "VectorEnv", "Trajectories", "run_experiment",
+           "run_experiment_exact"]

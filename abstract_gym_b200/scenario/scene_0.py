@@ -99,6 +99,33 @@ class BatchedScene:
         """Global cumulative counters of the newest all_reduce_stats() call."""
         return self._reducer.result()
 
+    # ---- checkpoint / resume (SURVEY 8f.4) --------------------------------------------------------
+    _STATE = ("step_reward", "flags", "step_ctr", "reset_ctr", "ep_len", "stats", "diag")
+
+    def state_dict(self):
+        """Everything a resumed run needs to continue bit for bit: joint angles, sticky reward / flags, the
+        Philox draw counters, episode lengths and counters, seed and global env offset (host copies)."""
+        d = {k: getattr(self, k).detach().cpu().clone() for k in self._STATE}
+        d["joint_1"], d["joint_2"] = self.robot.joint_1.detach().cpu().clone(), self.robot.joint_2.detach().cpu().clone()
+        d["meta"] = dict(seed=self.seed, env_id0=self.env_id0, n=self.n, max_reset_tries=self.max_reset_tries,
+                         link_1=float(self.robot.link_1), link_2=float(self.robot.link_2),
+                         target_c=(float(self.target_c.x), float(self.target_c.y)),
+                         target_j=[float(self.target_j[0]), float(self.target_j[1])], choose_j_tar=bool(self.choose_j_tar))
+        return d
+
+    def load_state_dict(self, d):
+        m = d["meta"]
+        if int(m["n"]) != self.n:
+            raise ValueError("checkpoint holds %d envs, this scene %d" % (m["n"], self.n))
+        for k in self._STATE:
+            getattr(self, k).copy_(d[k])
+        self.robot.joint_1.copy_(d["joint_1"]); self.robot.joint_2.copy_(d["joint_2"])
+        self.seed, self.env_id0, self.max_reset_tries = int(m["seed"]), int(m["env_id0"]), int(m["max_reset_tries"])
+        self.robot.link_1, self.robot.link_2 = m["link_1"], m["link_2"]
+        self.target_c = Point(*m["target_c"])
+        self.target_j = np.array(m["target_j"])
+        self.choose_j_tar = bool(m["choose_j_tar"])
+
     # ---- K2 ------------------------------------------------------------------------------------
     def collision_check(self, first_hit=False, engine=None):
         """scene_0.py:60-76 for every env -> bool [N] (and int32 [N] min hit cell index, -1 if none)."""

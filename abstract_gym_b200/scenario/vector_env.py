@@ -1,0 +1,126 @@
+"""Gym-style batched front end of scene_0 for RL training loops: the callers of
+`Scene.step` / `Scene.reset` (scenario/scene_0.py:88-113) want observations, rewards and termination flags
+for N environments per call, with terminated environments restarted automatically the way
+experiment/experiment_0.py:30-34 does.
+
+    env = VectorEnv(4096, device="cuda")
+    obs = env.reset()
+    obs, reward, terminated, truncated, info = env.step(action)      # action: [N, 2] joint deltas
+
+Observation [N, 6] float64: (joint_1, joint_2, EE_x, EE_y, |target_x - EE_x|, |target_y - EE_y|) -- the two
+quantities `check_target_reached` thresholds (scene_0.py:129-130) are the reference's only notion of goal distance.
+Every call is a fixed sequence of launches of the CUDA kernels behind the C ABI (K1 step, K3 masked reset, FK) on
+preallocated buffers, so `capture()` can record it once into a CUDA graph and `step` replays it.
+"""
+import torch
+
+from .. import _lib
+from .._device import ptr, require_cuda, stream_ptr
+from ..environment.occupancy_grid import OccupancyGrid
+from ..robot.two_joint_robot import BatchedTwoJointRobot
+from .scene_0 import BatchedScene
+
+
+class VectorEnv:
+    def __init__(self, num_envs, env=None, device=None, seed=0, engine="fast", auto_reset=True, target_c=None,
+                 choose_j_tar=False, env_id0=0):
+        dev = require_cuda(device)
+        self.num_envs = int(num_envs)
+        self.device = dev
+        self.auto_reset = bool(auto_reset)
+        grid = env if env is not None else OccupancyGrid(size=9, random_obstacle=False)      # scene_0's map
+        gen = torch.Generator(device=dev).manual_seed(int(seed))
+        robot = BatchedTwoJointRobot.random(self.num_envs, device=dev, generator=gen)
+        self.scene = BatchedScene(robot, grid, target_c=target_c, engine=engine, seed=seed, env_id0=env_id0)
+        self.scene.choose_j_tar = bool(choose_j_tar)
+        n = self.num_envs
+        self._action = torch.zeros(n, 2, dtype=torch.float64, device=dev)
+        self._ee = torch.zeros(n, 2, dtype=torch.float64, device=dev)
+        self._dist = torch.zeros(n, 2, dtype=torch.float64, device=dev)
+        self._fk = torch.zeros(n, 4, dtype=torch.float64, device=dev)
+        self._obs = torch.zeros(n, 6, dtype=torch.float64, device=dev)
+        self._final_obs = torch.zeros(n, 6, dtype=torch.float64, device=dev)
+        self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._terminated = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._collision = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._mask = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._graph = None
+        self._lib = _lib.load()
+
+    # ---- pieces (all on preallocated buffers: capturable) ----------------------------------------
+    def _observe(self, out):
+        sc = self.scene
+        _lib.check(self._lib.ag_forward_kinematics(sc.params(), ptr(sc.robot.joint_1), ptr(sc.robot.joint_2),
+                                                   ptr(self._fk), self.num_envs, stream_ptr(self.device)),
+                   "ag_forward_kinematics")
+        out[:, 0].copy_(sc.robot.joint_1); out[:, 1].copy_(sc.robot.joint_2)
+        out[:, 2:4].copy_(self._fk[:, 2:4])
+        out[:, 4].copy_((float(sc.target_c.x) - self._fk[:, 2]).abs())
+        out[:, 5].copy_((float(sc.target_c.y) - self._fk[:, 3]).abs())
+
+    def _step_impl(self):
+        sc = self.scene
+        g = sc.grid.c_struct()
+        _lib.check(self._lib.ag_step(sc.params(), g, ptr(sc.robot.joint_1), ptr(sc.robot.joint_2), ptr(self._action), 0,
+                                     ptr(sc.step_reward), ptr(sc.flags), ptr(self._ee), ptr(self._dist), None,
+                                     ptr(sc.stats), self.num_envs, sc.env_id0, sc.engine, stream_ptr(self.device)),
+                   "ag_step")
+        self._reward.copy_(sc.step_reward)
+        self._terminated.copy_(sc.flags != 0)
+        self._collision.copy_((sc.flags & _lib.FLAG_COLLISION) != 0)
+        fo = self._final_obs
+        fo[:, 0].copy_(sc.robot.joint_1); fo[:, 1].copy_(sc.robot.joint_2)
+        fo[:, 2:4].copy_(self._ee); fo[:, 4:6].copy_(self._dist)
+        if self.auto_reset:
+            self._mask.copy_(sc.flags != 0)
+            _lib.check(self._lib.ag_reset(sc.params(), g, ptr(sc.robot.joint_1), ptr(sc.robot.joint_2),
+                                          ptr(sc.step_reward), ptr(sc.flags), ptr(sc.reset_ctr), ptr(self._mask), None, 0,
+                                          sc.seed, 1, ptr(sc.stats), self.num_envs, sc.env_id0, sc.engine,
+                                          stream_ptr(self.device)), "ag_reset")
+            self._observe(self._obs)          # restarted envs show their first observation (same-step autoreset)
+        else:
+            self._obs.copy_(fo)
+
+    # ---- public API ------------------------------------------------------------------------------
+    def reset(self):
+        """Scene.random_valid_pose + Scene.reset for every env (experiment_0.py:16); returns obs [N, 6]."""
+        self.scene.random_valid_pose()
+        self.scene.reset()
+        self._observe(self._obs)
+        return self._obs
+
+    def capture(self):
+        """Record one step (K1 -> flag/reward extraction -> K3 -> FK/observation) into a CUDA graph."""
+        torch.cuda.synchronize(self.device)
+        snap = self.scene.state_dict()
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._step_impl()                # warm-up outside capture
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._step_impl()
+        self.scene.load_state_dict(snap)     # the warm-up and the capture advanced nothing the caller should see
+        torch.cuda.synchronize(self.device)
+        self._graph = graph
+        return self
+
+    def step(self, action):
+        """action: [N, 2] joint deltas (any float dtype).  Returns (obs, reward, terminated, truncated, info);
+        terminated = done | collision (experiment_0.py:30); truncated is always False (the reference has no time limit);
+        info: collision [N] bool, final_obs [N, 6] (the terminal observation of envs that were restarted)."""
+        self._action.copy_(torch.as_tensor(action, device=self.device).reshape(self.num_envs, 2))
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._step_impl()
+        return (self._obs, self._reward, self._terminated, torch.zeros_like(self._terminated),
+                dict(collision=self._collision, final_obs=self._final_obs))
+
+    def sample_action(self, scale_factor=0.1, generator=None):
+        return self.scene.sample_action(scale_factor, generator)
+
+    def stats(self):
+        return self.scene.stats_dict()

@@ -454,3 +454,57 @@ def test_experiment_drivers_fast_equals_exact(ag, torch_):
     assert np.array_equal(fast.flags, exact.flags) and np.array_equal(fast.reward, exact.reward)
     assert np.array_equal(fast.j1, exact.j1.astype(np.float32)) and np.array_equal(fast.j2, exact.j2.astype(np.float32))
     assert fast.episode_index().tolist() == exact.episode_index().tolist() and len(fast.episode_index()) > 20
+
+
+@pytest.mark.gpu
+def test_checkpoint_resume_is_bit_exact(ag, torch_, tmp_path):
+    """state_dict -> torch.save -> load_state_dict: the resumed rollout (in-kernel Philox actions and resets)
+    equals the uninterrupted one"""
+    n = 4096
+    rng = np.random.default_rng(31)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    a = make_scene(ag, torch_, g, j1, j2, seed=8, env_id0=1000)
+    a.rollout(24, record=False)
+    path = str(tmp_path / "ckpt.pt")
+    torch_.save(a.state_dict(), path)
+    ra = a.rollout(40)
+    b = make_scene(ag, torch_, g, np.zeros(n), np.zeros(n), seed=0)
+    b.load_state_dict(torch_.load(path))
+    rb = b.rollout(40)
+    for k in ("j1", "j2", "reward", "flags"):
+        assert torch_.equal(ra[k], rb[k]), k
+    assert torch_.equal(a.robot.joint_1, b.robot.joint_1) and torch_.equal(a.reset_ctr, b.reset_ctr)
+    assert a.stats_dict() == b.stats_dict() and a.stats_dict()["episodes"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_vector_env_matches_scene_loop(ag, torch_, oracle, graph):
+    """VectorEnv.step == BatchedScene.step + masked reset (the experiment_0 loop), eager and as a CUDA graph;
+    observations carry the float64 end effector and the goal distance of check_target_reached"""
+    n, T = 2048, 30
+    env = ag.VectorEnv(n, device="cuda", seed=5)
+    ref = ag.VectorEnv(n, device="cuda", seed=5)
+    obs0, obs0r = env.reset().clone(), ref.reset().clone()
+    assert torch_.equal(obs0, obs0r)
+    assert not bool(env.scene.collision_check().any())
+    ex, ey, gx, gy = oracle.forward_kinematics(float(obs0[7, 0]), float(obs0[7, 1]))
+    assert rel_close(obs0[7, 2:4].cpu().numpy(), np.array([gx, gy]))
+    assert rel_close(obs0[7, 4:6].cpu().numpy(), np.abs(np.array([-0.2 - gx, -0.3 - gy])))
+    if graph:
+        env.capture()
+    gen = torch_.Generator(device="cuda").manual_seed(17)
+    sc = ref.scene
+    n_term = 0
+    for t in range(T):
+        a = (torch_.rand(n, 2, dtype=torch_.float64, device="cuda", generator=gen) - 0.5) * 0.1
+        obs, rw, term, trunc, info = env.step(a)
+        j1, j2, r2, done, coll = sc.step(a)
+        assert torch_.equal(rw, r2) and torch_.equal(term, done | coll) and torch_.equal(info["collision"], coll)
+        assert torch_.equal(info["final_obs"][:, 0], j1) and not bool(trunc.any())
+        m = sc.flags != 0
+        n_term += int(m.sum().item())
+        sc.reset(mask=m)
+        assert torch_.equal(obs[:, 0], sc.robot.joint_1) and torch_.equal(obs[:, 1], sc.robot.joint_2)
+    assert n_term > 20 and env.stats() == ref.stats()
