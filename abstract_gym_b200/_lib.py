@@ -71,6 +71,8 @@ SYMBOLS = {
     "ag_grid_pack": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp]),
     "ag_segment_square": (_i32, [_vp, _vp, _dbl, _vp, _vp, _vp, _vp, _i64, _vp]),
     "ag_forward_kinematics": (_i32, [C.POINTER(Params), _vp, _vp, _vp, _i64, _vp]),
+    "ag_inverse_kinematics": (_i32, [C.POINTER(Params), _vp, _vp, _vp, _i32, _i64, _vp]),
+    "ag_move_to_joint_pose": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp]),
     "ag_collision_check": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     "ag_step": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                        _i64, _i64, _i32, _vp]),

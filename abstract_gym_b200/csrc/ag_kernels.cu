@@ -125,6 +125,47 @@ __global__ void k_forward_kinematics(ag_params P, const double *__restrict__ j1,
     reinterpret_cast<double4 *>(out)[i] = make_double4(A.ex, A.ey, A.gx, A.gy);
 }
 
+// robot/two_joint_robot.py:74-113 inverse_kinematic() over arrays (not on the step/reset path).
+// sol: [n][4] = (j1_1, j2_1, j1_2, j2_2); valid: [n].  corrected: alpha = atan2(y, x) instead of arccos(x/r).
+__global__ void k_inverse_kinematics(ag_params P, const double *__restrict__ target, double *__restrict__ sol,
+                                     uint8_t *__restrict__ valid, int corrected, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 t = reinterpret_cast<const double2 *>(target)[i];
+    const double l1 = P.link_1, l2 = P.link_2;
+    const double radius = sqrt(__dadd_rn(__dmul_rn(t.x, t.x), __dmul_rn(t.y, t.y)));                   // :82
+    const bool ok = (fabs(__dsub_rn(l1, l2)) < radius) && (radius <= __dadd_rn(l1, l2)) && radius != 0.0;   // :80-86,:96
+    valid[i] = ok ? 1 : 0;
+    double4 out = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (ok) {
+        const double r2 = __dmul_rn(radius, radius), a2 = __dmul_rn(l1, l1), b2 = __dmul_rn(l2, l2);
+        const double cos_theta = __ddiv_rn(__dsub_rn(__dadd_rn(r2, a2), b2), __dmul_rn(__dmul_rn(2.0, l1), radius));   // :99
+        const double theta = acos(cos_theta);                                                                        // :100
+        const double alpha = corrected ? atan2(t.y, t.x) : acos(__ddiv_rn(t.x, radius));                             // :101-102
+        const double cos_beta = __ddiv_rn(__dsub_rn(__dadd_rn(a2, b2), r2), __dmul_rn(__dmul_rn(2.0, l1), l2));      // :105
+        const double inner = __dsub_rn(3.141592653589793, acos(cos_beta));
+        out.x = __dsub_rn(alpha, theta);                                   // :103
+        out.z = __dadd_rn(alpha, theta);                                   // :104
+        out.y = __dadd_rn(inner, out.x);                                   // :106
+        out.w = __dsub_rn(out.z, inner);                                   // :107
+    }
+    reinterpret_cast<double4 *>(sol)[i] = out;
+}
+
+// robot/two_joint_robot.py:49-62 move_to_joint_pose(): `steps` increments alpha*(target - init) added one by one
+// (no intermediate collision checks, like the reference)
+__global__ void k_move_to_joint_pose(double *__restrict__ j1, double *__restrict__ j2, const double *__restrict__ target,
+                                     int steps, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 t = reinterpret_cast<const double2 *>(target)[i];
+    double a = j1[i], b = j2[i];
+    const double alpha = __ddiv_rn(1.0, (double)steps);                    // :57
+    const double inc1 = __dmul_rn(alpha, __dsub_rn(t.x, a)), inc2 = __dmul_rn(alpha, __dsub_rn(t.y, b));
+    for (int k = 0; k < steps; ++k) { a = __dadd_rn(a, inc1); b = __dadd_rn(b, inc2); }                 // :61-62
+    j1[i] = a; j2[i] = b;
+}
+
 // collision_check of one pose for K2/K3 (flag only unless WANT_FIRST)
 template <int ENGINE, bool WANT_FIRST, int BP = BP_ANY, bool COLD = false>
 __device__ __forceinline__ bool pose_collides(const ag_params &P, const GridDev &G, const BlockCtx &B,
@@ -698,6 +739,25 @@ ag_status ag_forward_kinematics(const ag_params *p, const double *j1, const doub
     if (!p || !j1 || !j2 || !out) return AG_ERR_NULL;
     if ((uintptr_t)out % 32) return AG_ERR_ALIGN;
     k_forward_kinematics<<<blocks_for(n), AG_BLOCK, 0, (cudaStream_t)stream>>>(*p, j1, j2, out, n);
+    return launched();
+}
+
+ag_status ag_inverse_kinematics(const ag_params *p, const double *target, double *sol, uint8_t *valid, int32_t corrected,
+                                int64_t n, void *stream) {
+    if (n < 0) return AG_ERR_SHAPE;
+    if (n == 0) return AG_OK;
+    if (!p || !target || !sol || !valid) return AG_ERR_NULL;
+    if (((uintptr_t)target % 16) || ((uintptr_t)sol % 32)) return AG_ERR_ALIGN;
+    k_inverse_kinematics<<<blocks_for(n), AG_BLOCK, 0, (cudaStream_t)stream>>>(*p, target, sol, valid, corrected, n);
+    return launched();
+}
+
+ag_status ag_move_to_joint_pose(double *j1, double *j2, const double *target, int32_t steps, int64_t n, void *stream) {
+    if (n < 0 || steps < 1) return AG_ERR_SHAPE;
+    if (n == 0) return AG_OK;
+    if (!j1 || !j2 || !target) return AG_ERR_NULL;
+    if ((uintptr_t)target % 16) return AG_ERR_ALIGN;
+    k_move_to_joint_pose<<<blocks_for(n), AG_BLOCK, 0, (cudaStream_t)stream>>>(j1, j2, target, steps, n);
     return launched();
 }
 

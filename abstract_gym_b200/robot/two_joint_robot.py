@@ -147,3 +147,23 @@ class BatchedTwoJointRobot:
     def move_delta(self, d1, d2):
         self.joint_1 += as_f64(d1, self.device)
         self.joint_2 += as_f64(d2, self.device)
+
+    # ---- not on the step/reset path ---------------------------------------------------
+    def move_to_joint_pose(self, target, steps=100):
+        """robot/two_joint_robot.py:49-62 for every arm: target [N,2] joint poses, `steps` equal increments."""
+        t = as_f64(target, self.device).reshape(len(self), 2).contiguous()
+        _lib.check(_lib.load().ag_move_to_joint_pose(ptr(self.joint_1), ptr(self.joint_2), ptr(t), int(steps), len(self),
+                                                     stream_ptr(self.device)), "ag_move_to_joint_pose")
+
+    def inverse_kinematic(self, target_c, corrected=False):
+        """robot/two_joint_robot.py:88-113 for M cartesian targets [M,2] -> (valid [M] bool, s1 [M,2], s2 [M,2]).
+        Unreachable targets (the reference returns None, None) have valid == False and zero solutions.
+        corrected=True uses atan2(y, x) for alpha; the reference's arccos(x/r) loses the sign of y."""
+        t = as_f64(target_c, self.device).reshape(-1, 2).contiguous()
+        m = t.shape[0]
+        sol = torch.empty(m, 4, dtype=torch.float64, device=self.device)
+        valid = torch.empty(m, dtype=torch.uint8, device=self.device)
+        _lib.check(_lib.load().ag_inverse_kinematics(_params_for(self.link_1, self.link_2), ptr(t), ptr(sol), ptr(valid),
+                                                     1 if corrected else 0, m, stream_ptr(self.device)),
+                   "ag_inverse_kinematics")
+        return valid != 0, sol[:, 0:2], sol[:, 2:4]

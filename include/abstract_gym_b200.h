@@ -146,6 +146,17 @@ AG_API ag_status ag_segment_square(const double *seg, const double *sq, double s
 AG_API ag_status ag_forward_kinematics(const ag_params *p, const double *j1, const double *j2, double *out,
                                 int64_t n, void *stream);
 
+/* robot/two_joint_robot.py:74-113  cart_target_valid_check() + inverse_kinematic() over arrays (off the step/reset
+ * path).  target: [n][2]; sol: [n][4] = (j1_1, j2_1, j1_2, j2_2), zeros where valid[i] == 0 (target outside the
+ * annulus |l1-l2| < r <= l1+l2: the reference prints "Target out of reach." and returns None).
+ * corrected != 0: alpha = atan2(y, x) instead of the reference's arccos(x/r), which drops the sign of y. */
+AG_API ag_status ag_inverse_kinematics(const ag_params *p, const double *target, double *sol, uint8_t *valid,
+                                int32_t corrected, int64_t n, void *stream);
+
+/* robot/two_joint_robot.py:49-62  move_to_joint_pose(target_j1, target_j2, steps): target [n][2]; j1, j2 in/out. */
+AG_API ag_status ag_move_to_joint_pose(double *j1, double *j2, const double *target, int32_t steps, int64_t n,
+                                void *stream);
+
 /* K2: scenario/scene_0.py:60-76  Scene.collision_check().  hit: [n] uint8; first_hit: optional
  * [n] int32 = min(row*S+col) over all cells hit by either link, -1 if none. */
 AG_API ag_status ag_collision_check(const ag_params *p, const ag_grid *g, const double *j1, const double *j2,

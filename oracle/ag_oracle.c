@@ -178,6 +178,47 @@ void ago_forward_kinematics(double j1, double j2, double l1, double l2,
     *ee_y = sin(j1) * l1 + sin(j2) * l2;                 /* :37 */
 }
 
+/* ------------------------------------------------------------------ IK / joint-space motion */
+
+/* robot/two_joint_robot.py:74-113.  sol = (j1_1, j2_1, j1_2, j2_2); returns 1 if the target is in the reachable
+ * annulus |l1-l2| < r <= l1+l2 (and r != 0), else 0 with sol untouched.  corrected != 0 replaces
+ * alpha = arccos(x/r) (which drops the sign of y) by atan2(y, x).
+ * Pinned to the reference within 4 ulp, not bit-exact: numpy's arccos is not glibc's acos (tests/test_oracle_golden.py). */
+/* the reference squares with pow(x, 2) (Python float / numpy scalar __pow__ -> libm pow); gcc would fold a literal
+ * exponent into x*x, which is not always the same double, so the exponent is kept opaque */
+static double pw2(double x) {
+    volatile double two = 2.0;
+    return pow(x, two);
+}
+
+int ago_inverse_kinematics(double tx, double ty, double l1, double l2, int corrected, double *sol) {
+    const double R = l1 + l2;                                           /* :80 total_length() */
+    const double r = fabs(l1 - l2);                                     /* :81 */
+    const double radius = sqrt(pw2(tx) + pw2(ty));                      /* :82 */
+    if (!(r < radius && radius <= R)) return 0;                         /* :83-86 */
+    if (radius == 0) return 0;                                          /* :96-98 */
+    const double cos_theta = (pw2(radius) + pw2(l1) - pw2(l2)) / (2.0 * l1 * radius);   /* :99 */
+    const double theta = acos(cos_theta);                               /* :100 */
+    const double alpha = corrected ? atan2(ty, tx) : acos(tx / radius); /* :101-102 */
+    const double j1_1 = alpha - theta, j1_2 = alpha + theta;            /* :103-104 */
+    const double cos_beta = (pw2(l1) + pw2(l2) - pw2(radius)) / (2.0 * l1 * l2);        /* :105 */
+    sol[0] = j1_1;
+    sol[1] = M_PI - acos(cos_beta) + j1_1;                              /* :106 */
+    sol[2] = j1_2;
+    sol[3] = j1_2 - (M_PI - acos(cos_beta));                            /* :107 */
+    return 1;
+}
+
+/* robot/two_joint_robot.py:49-62: `steps` equal increments alpha*(target - init), accumulated one by one */
+void ago_move_to_joint_pose(double *j1, double *j2, double t1, double t2, int32_t steps) {
+    const double alpha = 1.0 / steps;                                   /* :57 */
+    const double i1 = *j1, i2 = *j2;
+    for (int32_t i = 0; i < steps; ++i) {
+        *j1 += alpha * (t1 - i1);                                       /* :61 */
+        *j2 += alpha * (t2 - i2);                                       /* :62 */
+    }
+}
+
 /* ------------------------------------------------------------------ scene (C1,R1,ST,RS) */
 
 int ago_collision_check(const ago_params *p, double j1, double j2, const ago_square *sq,

@@ -130,6 +130,21 @@ def forward_kinematics(j1, j2, l1=0.4, l2=0.3):
     return tuple(x.value for x in o)
 
 
+def inverse_kinematics(tx, ty, l1=0.4, l2=0.3, corrected=False):
+    """-> (valid, [j1_1, j2_1, j1_2, j2_2])"""
+    sol = (C.c_double * 4)()
+    lib().ago_inverse_kinematics.restype = C.c_int
+    ok = lib().ago_inverse_kinematics(C.c_double(tx), C.c_double(ty), C.c_double(l1), C.c_double(l2),
+                                      C.c_int(1 if corrected else 0), sol)
+    return bool(ok), [sol[i] for i in range(4)]
+
+
+def move_to_joint_pose(j1, j2, t1, t2, steps=100):
+    a, b = C.c_double(j1), C.c_double(j2)
+    lib().ago_move_to_joint_pose(C.byref(a), C.byref(b), C.c_double(t1), C.c_double(t2), C.c_int32(steps))
+    return a.value, b.value
+
+
 def collision_batch(j1, j2, squares, cell_index=None, params=None, want_first_hit=True, want_margin=False):
     p = params or default_params()
     j1 = np.ascontiguousarray(j1, dtype=np.float64)

@@ -508,3 +508,31 @@ def test_vector_env_matches_scene_loop(ag, torch_, oracle, graph):
         sc.reset(mask=m)
         assert torch_.equal(obs[:, 0], sc.robot.joint_1) and torch_.equal(obs[:, 1], sc.robot.joint_2)
     assert n_term > 20 and env.stats() == ref.stats()
+
+
+@pytest.mark.gpu
+def test_batched_ik_and_move_to_joint_pose_vs_reference(ag, torch_, golden_dir):
+    """robot/two_joint_robot.py:49-113 over arrays vs fixtures from the live reference: reachability flags
+    equal, joint solutions within 1e-12 (north_star asks 1e-5 relative), move_to_joint_pose bit-exact"""
+    z = np.load(os.path.join(golden_dir, "ik_cases.npz"))
+    rb = ag.BatchedTwoJointRobot(torch_.zeros(1, dtype=torch_.float64, device="cuda"),
+                                 torch_.zeros(1, dtype=torch_.float64, device="cuda"))
+    valid, s1, s2 = rb.inverse_kinematic(torch_.as_tensor(z["target"], device="cuda"))
+    v = valid.cpu().numpy()
+    assert np.array_equal(v, z["valid"] != 0)
+    sol = np.concatenate([s1.cpu().numpy(), s2.cpu().numpy()], axis=1)
+    assert np.max(np.abs(sol[v] - z["sol"][v])) < 1e-12 and np.all(sol[~v] == 0)
+    # corrected variant: FK of the solution lands on the target also for y < 0
+    tgt = z["target"][v]
+    _, c1, c2 = rb.inverse_kinematic(torch_.as_tensor(tgt, device="cuda"), corrected=True)
+    for c in (c1, c2):
+        ee = ag.forward_kinematics(c[:, 0].contiguous(), c[:, 1].contiguous())[:, 2:4].cpu().numpy()
+        assert np.max(np.abs(ee - tgt)) < 1e-7      # acos is ill-conditioned at the rim of the annulus (sqrt(eps))
+    # one launch per distinct step count (steps is a launch parameter)
+    for st in np.unique(z["steps"]):
+        sel = np.nonzero(z["steps"] == st)[0]
+        sub = ag.BatchedTwoJointRobot(torch_.as_tensor(z["start"][sel, 0].copy(), device="cuda"),
+                                      torch_.as_tensor(z["start"][sel, 1].copy(), device="cuda"))
+        sub.move_to_joint_pose(torch_.as_tensor(z["goal"][sel].copy(), device="cuda"), steps=int(st))
+        assert np.array_equal(sub.joint_1.cpu().numpy(), z["end"][sel, 0])
+        assert np.array_equal(sub.joint_2.cpu().numpy(), z["end"][sel, 1])

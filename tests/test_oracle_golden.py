@@ -163,3 +163,27 @@ def test_philox_known_answers(oracle):
         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
     u = oracle.philox_uniform2(7, 123456789012, 5, 1)
     assert 0.0 <= u[0] < 1.0 and 0.0 <= u[1] < 1.0 and u[0] != u[1]
+
+
+def test_ik_and_move_to_joint_pose_goldens(oracle, golden_dir):
+    """robot/two_joint_robot.py:49-113 vs fixtures from the live reference (oracle/make_golden_ik.py).
+    move_to_joint_pose and the reachability test are bit-exact; the IK angles agree to 4 ulp of pi: numpy's
+    float64 arccos is its own SIMD implementation and differs from glibc's acos by 1 ulp on 9 % of arguments
+    (measured here), so the C restatement cannot be bit-identical off the hot path."""
+    z = np.load(os.path.join(golden_dir, "ik_cases.npz"))
+    t, valid, sol = z["target"], z["valid"], z["sol"]
+    assert 1000 < int(valid.sum()) < len(valid)
+    for i in range(len(t)):
+        ok, s = oracle.inverse_kinematics(float(t[i, 0]), float(t[i, 1]))
+        assert ok == bool(valid[i]), (i, t[i])
+        if ok:
+            assert np.max(np.abs(np.array(s) - sol[i])) <= 4 * 4.45e-16, (i, t[i], s, sol[i])
+    ok, s = oracle.inverse_kinematics(0.5, 0.0)                 # the reference's __main__ known answer (SURVEY section 4)
+    assert ok and np.allclose(s, [-0.64350111, 0.92729522, 0.64350111, -0.92729522], atol=5e-9)
+    ok, s = oracle.inverse_kinematics(-0.2, -0.3, corrected=True)
+    ex, ey, gx, gy = oracle.forward_kinematics(s[0], s[1])
+    assert abs(gx + 0.2) < 1e-12 and abs(gy + 0.3) < 1e-12      # atan2 variant reaches targets with y < 0
+    for i in range(len(z["steps"])):
+        e1, e2 = oracle.move_to_joint_pose(z["start"][i, 0], z["start"][i, 1], z["goal"][i, 0], z["goal"][i, 1],
+                                           int(z["steps"][i]))
+        assert [e1, e2] == z["end"][i].tolist()
