@@ -18,6 +18,17 @@ def shard_range(n_total: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def nccl_options():
+    """NCCL on a high-priority stream: the statistics all-reduce is a tiny kernel that must slip in between
+    the blocks of a rollout kernel that fills every SM, not wait for it to drain."""
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        return opts
+    except Exception:
+        return None
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from torchrun's environment (RANK/WORLD_SIZE/MASTER_*).
     Returns (rank, world, local_rank); a single process needs no process group."""
@@ -29,7 +40,9 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend)
+            dist.init_process_group(backend=backend, pg_options=nccl_options(), device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend=backend)
     return rank, world, local
 
 
@@ -47,27 +60,35 @@ class StatsReducer:
 
     After every rollout launch `submit(local_stats)` snapshots this rank's cumulative counters
     (stream-ordered after the kernel) and starts their all-reduce with async_op=True: NCCL runs it
-    on its own stream, so the next rollout kernel is not queued behind the collective.  `result()`
-    waits for the newest submitted reduction and returns the global cumulative totals."""
+    on its own stream, so the next rollout kernel is not queued behind the collective.  Up to
+    `depth` reductions stay in flight (the collective's tiny kernel may only get an SM slot when
+    the rollout kernel that was launched right behind it drains).  `result()` waits for the newest
+    submitted reduction and returns the global cumulative totals."""
 
-    def __init__(self):
-        self._buf = None
-        self._work = None
+    def __init__(self, depth: int = 2):
+        self._depth = max(1, int(depth))
+        self._pending = []          # [(buffer, work)] oldest first
 
     def submit(self, local_stats: torch.Tensor) -> None:
-        if self._work is not None:
-            self._work.wait()                 # at most one reduction in flight; it overlapped the last kernel
+        while len(self._pending) >= self._depth:
+            _, work = self._pending.pop(0)
+            if work is not None:
+                work.wait()         # stream-level wait; it had `depth` launches to finish
         buf = local_stats.clone()
-        self._buf = buf
-        self._work = None
+        work = None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self._work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
+            work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
+        self._pending.append((buf, work))
 
     def result(self) -> torch.Tensor:
-        if self._work is not None:
-            self._work.wait()
-            self._work = None
-        return self._buf
+        if not self._pending:
+            return None
+        for _, work in self._pending:
+            if work is not None:
+                work.wait()
+        buf = self._pending[-1][0]
+        self._pending = [(buf, None)]
+        return buf
 
 
 def max_over_ranks(value: float, device=None) -> float:

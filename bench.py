@@ -332,7 +332,8 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        from abstract_gym_b200.sharding import nccl_options
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local), pg_options=nccl_options())
     run_ours(args, rank, world, local)
     if world > 1:
         import torch.distributed as dist
