@@ -16,6 +16,7 @@ from .robot.two_joint_robot import TwoJointRobot, BatchedTwoJointRobot, forward_
 from .environment.occupancy_grid import OccupancyGrid, BatchedOccupancyGrid, DeviceGrid
 from .scenario.scene_0 import Scene, BatchedScene
 from .scenario.vector_env import VectorEnv
+from . import ops          # registers torch.ops.abstract_gym_b200.{collision_check, step, reset, rollout}
 from .experiment.experiment_0 import Trajectories, run_experiment, run_experiment_exact
 
 __all__ = ["AgError", "ENGINES", "STAT_NAMES", "default_params", "launch_count", "Point", "Line", "Square",

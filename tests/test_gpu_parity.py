@@ -568,3 +568,42 @@ def test_tangency_band_all_engines_and_oracle(ag, torch_, oracle):
           % (int(bad.sum()), n, float(mg[bad].max()) if bad.any() else 0.0, int(hard.sum())))
     assert int(hard.sum()) == 0 and int(bad.sum()) <= 32 and (not bad.any() or float(mg[bad].max()) < 1e-12)
     assert 0.05 < res["exact"].mean() < 0.95
+
+
+@pytest.mark.gpu
+def test_torch_custom_ops_equal_object_api(ag, torch_):
+    """torch.ops.abstract_gym_b200.* (functional front end over the same C symbols) == BatchedScene"""
+    from abstract_gym_b200 import ops
+    n, K = 3000, 20
+    rng = np.random.default_rng(41)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = torch_.as_tensor(((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32), device="cuda")
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    ref = make_scene(ag, torch_, g, j1, j2, seed=3)
+    rec = ref.rollout(K, actions=acts)
+    sc = make_scene(ag, torch_, g, j1, j2, seed=3)         # only used as a bag of correctly typed state tensors
+    dg = sc.grid
+    P, M = ops.pack_params(sc.params()), ops.pack_grid_meta(dg)
+    out = sc.alloc_records(K)
+    hit = torch_.empty(n, dtype=torch_.uint8, device="cuda")
+    torch_.ops.abstract_gym_b200.collision_check(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1, sc.robot.joint_2,
+                                                 hit, 0, 1)
+    assert torch_.equal(hit != 0, ref.__class__.collision_check(make_scene(ag, torch_, g, j1, j2)))
+    torch_.ops.abstract_gym_b200.rollout(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1, sc.robot.joint_2,
+                                         sc.step_reward, sc.flags, sc.step_ctr, sc.reset_ctr, sc.ep_len, acts,
+                                         out["j1"], out["j2"], out["reward"], out["flags"], sc.stats, 3, 0, 1)
+    for k in ("j1", "j2", "reward", "flags"):
+        assert torch_.equal(rec[k], out[k]), k
+    assert torch_.equal(ref.stats, sc.stats) and torch_.equal(ref.robot.joint_1, sc.robot.joint_1)
+    # one step + masked reset through the ops == through the object API
+    a1 = (torch_.rand(n, 2, dtype=torch_.float64, device="cuda") - 0.5) * 0.1
+    ref.step(a1); m = (ref.flags != 0).to(torch_.uint8); ref.reset(mask=m)
+    torch_.ops.abstract_gym_b200.step(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1, sc.robot.joint_2, a1,
+                                      sc.step_reward, sc.flags, sc.stats, 0, 1)
+    m2 = (sc.flags != 0).to(torch_.uint8)
+    torch_.ops.abstract_gym_b200.reset(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1, sc.robot.joint_2,
+                                       sc.step_reward, sc.flags, sc.reset_ctr, m2, sc.stats, 3, 0, 1)
+    assert torch_.equal(m, m2) and torch_.equal(ref.robot.joint_1, sc.robot.joint_1) and torch_.equal(ref.stats, sc.stats)
+    with pytest.raises(RuntimeError):
+        torch_.ops.abstract_gym_b200.collision_check(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1.cpu(),
+                                                     sc.robot.joint_2, hit, 0, 1)
