@@ -225,9 +225,12 @@ template <int ENGINE, bool WANT_FIRST>
 __device__ __forceinline__ bool arm_collides(const GridDev &G, const GridView &V, const Arm &A, double eps, int &fh,
                                              int &axis) {
     if (ENGINE == AG_ENGINE_BRUTE) return arm_brute<WANT_FIRST>(G, V, A, eps, fh, axis);
+    // reconverge between the two lane-dependent traversals (see arm_fast in ag_fast.cuh)
+    const unsigned lanes = __activemask();
     bool hit = link_exact<WANT_FIRST>(G, V, 0.0, 0.0, A.ex, A.ey, eps, fh, axis);
-    if (hit && !WANT_FIRST) return true;
-    hit |= link_exact<WANT_FIRST>(G, V, A.ex, A.ey, A.gx, A.gy, eps, fh, axis);
+    __syncwarp(lanes);
+    if (!hit || WANT_FIRST) hit |= link_exact<WANT_FIRST>(G, V, A.ex, A.ey, A.gx, A.gy, eps, fh, axis);
+    __syncwarp(lanes);
     return hit;
 }
 

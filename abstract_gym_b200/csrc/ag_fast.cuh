@@ -345,11 +345,16 @@ __device__ __forceinline__ int arm_fast(const GridDev &G, const GridView &V, con
                                         const ArmF &a) {
     if (BP == BP_LIST) return (fl != nullptr && fl->m >= 0) ? arm_fast_list(fl, a, C) : 2;
     if (BP == BP_ANY && fl != nullptr && fl->m >= 0) return arm_fast_list(fl, a, C);
+    // The two traversals have lane-dependent trip counts.  Without an explicit reconvergence point between them
+    // the lanes that finish link 1 first run ahead ALONE into link 2 (independent thread scheduling): ncu showed
+    // link 2's row loop at 1.0 active thread per instruction (profiles/r1_c4_*).  Hence: no early return between
+    // the links, and a __syncwarp over the lanes that entered together.
+    const unsigned lanes = __activemask();
     const int v1 = link_fast(G, V, C, 0.0f, 0.0f, a.ex, a.ey);
-    if (v1 == 1) return 1;
-    const int v2 = link_fast(G, V, C, a.ex, a.ey, a.gx, a.gy);
-    if (v2 == 1) return 1;
-    return v1 | v2;
+    __syncwarp(lanes);
+    const int v2 = (v1 == 1) ? 0 : link_fast(G, V, C, a.ex, a.ey, a.gx, a.gy);
+    __syncwarp(lanes);
+    return (v1 == 1 || v2 == 1) ? 1 : (v1 | v2);
 }
 
 // reach test filter, scenario/scene_0.py:129-130 ; 0/1 certain, 2 undecided

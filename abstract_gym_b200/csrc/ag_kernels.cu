@@ -566,6 +566,103 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
     }
 }
 
+// ------------------------------------------------------------------------------------------- K4, dense maps
+// Lane-asynchronous form of the same loop for grids that go through the cell traversal (high-resolution
+// and per-batch maps, BASELINE configs 4/5).  There an episode ends every second or third step and
+// Scene.reset() needs ~3 candidates on average, so a warp-synchronous kernel idles most lanes: a step
+// costs 1 pose check but the warp waits for the slowest lane's rejection loop (the maximum of 32 geometric
+// draws, ~9 checks).  Here every lane is a small state machine -- STEP (consume the action of its own step t)
+// or RESET (consume its next reset candidate) -- and each loop iteration runs exactly ONE pose check per lane,
+// so the expensive part (FK + traversal + narrow phase) is executed by all 32 lanes together whatever their
+// mode.  Lanes drift apart in t, so action loads / record stores are per-lane (sector-granular); this path
+// is bound by the traversal (thousands of instructions per check), not by memory.
+template <int BP, bool HAS_ACT, bool HAS_RESET_U, bool RECORD>
+__global__ void __launch_bounds__(AG_BLOCK, 2)
+k_rollout_async(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G, const __grid_constant__ FastConst C,
+                const __grid_constant__ RolloutDev A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ FastList s_fl;
+    __shared__ unsigned long long s_acc[AG_ST_COUNT + AG_DIAG_COUNT];
+    if (threadIdx.x < AG_ST_COUNT + AG_DIAG_COUNT) s_acc[threadIdx.x] = 0;
+    const BlockCtx B = block_prologue<AG_ENGINE_FAST>(G, A.env_id0, A.n, smem, &s_fl);
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    long long loc[AG_ST_COUNT];
+#pragma unroll
+    for (int i = 0; i < AG_ST_COUNT; ++i) loc[i] = 0;
+    if (e < A.n) {
+        double q1 = A.j1[e], q2 = A.j2[e];
+        float rw = A.reward[e];
+        uint32_t fl = A.flags[e], el = A.ep_len[e], rc = A.reset_ctr[e];
+        const uint32_t sc0 = A.step_ctr[e];
+        A.step_ctr[e] = sc0 + (uint32_t)A.K;
+        const uint64_t gid = (uint64_t)(A.env_id0 + e);
+        const double *ru = HAS_RESET_U ? A.reset_u + e * A.R * 2 : nullptr;
+        int t = 0, tries = 0;
+        bool resetting = false;
+        while (t < A.K || resetting) {
+            const unsigned live = __activemask();                                // the lanes still in the loop
+            bool stuck = false;
+            if (!resetting) {                                                    // ---- STEP: experiment_0.py:21-22
+                double d1, d2;
+                if (HAS_ACT) {
+                    const float2 a = __ldcs(reinterpret_cast<const float2 *>(A.actions) + (int64_t)t * A.row_stride + e);
+                    d1 = (double)a.x; d2 = (double)a.y;
+                } else {
+                    double u0, u1;
+                    philox_uniform2(A.seed, gid, sc0 + (uint32_t)t, 0u, u0, u1);
+                    d1 = __dmul_rn(__dsub_rn(u0, 0.5), P.action_scale);          // scene_0.py:84
+                    d2 = __dmul_rn(__dsub_rn(u1, 0.5), P.action_scale);          // :85
+                }
+                q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);                  // two_joint_robot.py:71-72
+            } else if (tries >= P.max_reset_tries || (HAS_RESET_U && rc >= (uint32_t)A.R)) {
+                stuck = true;                                                    // give up: keep the last candidate
+            } else {                                                             // ---- RESET: scene_0.py:179-181
+                double u0, u1;
+                if (HAS_RESET_U) {
+                    const double2 u = reinterpret_cast<const double2 *>(ru)[rc];
+                    u0 = u.x; u1 = u.y;
+                } else {
+                    philox_uniform2(A.seed, gid, rc, 1u, u0, u1);
+                }
+                ++rc; ++tries;
+                q1 = __dmul_rn(__dmul_rn(u0, 3.141592653589793), 2.0);           // scene_0.py:180  rand()*pi*2.0
+                q2 = __dmul_rn(__dmul_rn(u1, 3.141592653589793), 2.0);           // :181
+            }
+            // ---- one pose check per lane and iteration, whatever the mode, with all lanes converged
+            __syncwarp(live);
+            const int d = stuck ? 0 : fast_decide<BP>(P, G, B.V, B.fl, C, q1, q2, !resetting);
+            __syncwarp(live);
+            loc[AG_ST_AXIS_ALIGNED] += d >> 2;
+            if (!resetting) {
+                if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
+                if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
+                store_record<RECORD>(A, (int64_t)t * A.row_stride + e, q1, q2, rw, fl);    // experiment_0.py:23-25
+                ++el; ++t;
+                if (fl) {                                                        // experiment_0.py:30-34
+                    ++loc[AG_ST_EPISODES];
+                    loc[AG_ST_COLLISIONS] += (fl & AG_FLAG_COLLISION) ? 1 : 0;
+                    loc[AG_ST_SUCCESSES] += (fl & AG_FLAG_DONE) ? 1 : 0;
+                    loc[AG_ST_EP_LEN_SUM] += el;
+                    loc[AG_ST_RETURN_MILLI] += __float2int_rn(rw * 1e-3f);
+                    rw = 0.0f; fl = 0; el = 0;                                   // scene_0.py:111-113
+                    resetting = (d & 1) != 0;                                    // random_valid_pose() only while colliding
+                    tries = 0;
+                }
+            } else if (stuck) {
+                ++loc[AG_ST_STUCK_RESETS];
+                resetting = false;
+            } else if (!(d & 1)) {
+                resetting = false;                                               // candidate accepted
+            }
+        }
+        loc[AG_ST_ENV_STEPS] = A.K;
+        A.j1[e] = q1; A.j2[e] = q2; A.reward[e] = rw; A.flags[e] = (uint8_t)fl;
+        A.ep_len[e] = el; A.reset_ctr[e] = rc;
+    }
+    block_accumulate_stats(loc, A.stats, s_acc);
+}
+
 // ------------------------------------------------------------------------------------- host side
 int stage_max_bytes() {
     static int v = [] {
@@ -647,6 +744,13 @@ constexpr int AG_SMALL_BLOCK =
 
 template <int E, int BP, bool HA, bool HR, bool REC>
 ag_status launch_rollout_t(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s) {
+    if constexpr (E == AG_ENGINE_FAST && BP == BP_TRAVERSAL) {       // dense maps: lane-asynchronous kernel
+        auto k = k_rollout_async<BP, HA, HR, REC>;
+        ag_status st = set_smem(k, smem);
+        if (st) return st;
+        k<<<blocks_for(A.n), AG_BLOCK, smem, s>>>(P, G, make_fast_const(P, G), A);
+        return launched();
+    }
     if (E == AG_ENGINE_FAST && BP == BP_LIST && G.n_grids == 1) {
         // complete warps only (n % 32 == 0): the warp votes use a constant full mask
         if (A.n % 32 == 0)
