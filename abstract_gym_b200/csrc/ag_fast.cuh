@@ -285,6 +285,35 @@ __device__ __forceinline__ int arm_fast_list(const FastList *fl, const ArmF &a, 
 // only come out lower and the high index only higher (no F2I/FRND on the XU pipe).
 __device__ __forceinline__ int round_magic(float v) { return __float_as_int(v + 12582912.0f) - 0x4B400000; }
 
+// occupied cells of row r in columns [c_lo, c_hi] -> narrow phase; true = certain hit (result accumulates 0 / 2)
+struct LinkScan {
+    float p0x, p0y, p1x, p1y, side;
+    LinkF L;
+    bool have_link;
+    int result;
+};
+
+__device__ __forceinline__ bool scan_row(const GridView &V, const uint32_t *__restrict__ rowp, int r, int c_lo, int c_hi,
+                                         LinkScan &K) {
+    const int w0 = c_lo >> 5, w1 = c_hi >> 5;
+    const uint32_t mlo = 0xFFFFFFFFu << (c_lo & 31), mhi = 0xFFFFFFFFu >> (31 - (c_hi & 31));
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t word = rowp[w];
+        if (w == w0) word &= mlo;
+        if (w == w1) word &= mhi;
+        while (word) {
+            const int c = (w << 5) + __ffs(word) - 1;
+            word &= word - 1;
+            if (!K.have_link) { K.L = make_link_f(K.p0x, K.p0y, K.p1x, K.p1y, K.side); K.have_link = true; }
+            const float mnx = (float)V.min_x[c], mny = (float)V.min_y[r];
+            const int v = narrow_f32(K.L, mnx, mny, mnx + K.side, mny + K.side);
+            if (v == 1) return true;
+            K.result |= v;          // 0 or 2
+        }
+    }
+    return false;
+}
+
 __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, const FastConst &C, float p0x, float p0y,
                                          float p1x, float p1y) {
     const float mcell = fmaxf(2.0e-6f * C.inv_side, 1.0e-3f) + 0.001f;   // margin in cells
@@ -296,43 +325,40 @@ __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, co
     if (r_lo > S1 || r_hi < 0) return 0;
     r_lo = max(r_lo, 0); r_hi = min(r_hi, S1);
     const float dx = p1x - p0x, dy = p1y - p0y;
-    const bool clip = (r_hi - r_lo >= 2) && (fabsf(dy) * 64.0f >= fabsf(dx));
-    const float inv_dy = clip ? __frcp_rn(dy) : 0.0f;
-    const float mxcell = clip ? mcell + 5.0e-5f * C.inv_side : mcell;
-    const float xoff = C.half * C.inv_side - 0.5f;
-    int result = 0;
-    bool have_link = false;
-    LinkF L;
-    float yb = C.half - (float)r_lo * C.side;       // bottom edge of row r
-    for (int r = r_lo; r <= r_hi; ++r, yb -= C.side) {
-        float xa = p0x, xb = p1x;
-        if (clip) {
-            const float m = mcell * C.side;
-            const float t0 = (yb - m - p0y) * inv_dy, t1 = (yb + C.side + m - p0y) * inv_dy;
-            const float ta = __saturatef(fminf(t0, t1)), tb = __saturatef(fmaxf(t0, t1));
-            xa = fmaf(ta, dx, p0x); xb = fmaf(tb, dx, p0x);
-        }
-        int c_lo = round_magic(fmaf(fminf(xa, xb), C.inv_side, xoff - mxcell));
-        int c_hi = round_magic(fmaf(fmaxf(xa, xb), C.inv_side, xoff + mxcell));
-        if (c_lo > S1 || c_hi < 0) continue;
-        c_lo = max(c_lo, 0); c_hi = min(c_hi, S1);
-        for (int w = c_lo >> 5; w <= (c_hi >> 5); ++w) {
-            uint32_t mask = 0xFFFFFFFFu;
-            if (w == (c_lo >> 5)) mask &= 0xFFFFFFFFu << (c_lo & 31);
-            if (w == (c_hi >> 5)) mask &= 0xFFFFFFFFu >> (31 - (c_hi & 31));
-            uint32_t word = V.bits[r * G.wpr + w] & mask;
-            while (word) {
-                const int c = (w << 5) + __ffs(word) - 1;
-                word &= word - 1;
-                if (!have_link) { L = make_link_f(p0x, p0y, p1x, p1y, C.side); have_link = true; }
-                const float mnx = (float)V.min_x[c], mny = (float)V.min_y[r];
-                const int v = narrow_f32(L, mnx, mny, mnx + C.side, mny + C.side);
-                if (v == 1) return 1;
-                result |= v;          // 0 or 2
-            }
-        }
+    const float xoff = C.half * C.inv_side - 0.5f;      // column of x = round((x + half)/side - 0.5) = round(x*inv_side + xoff)
+    const float useg_lo = fmaf(fminf(p0x, p1x), C.inv_side, xoff), useg_hi = fmaf(fmaxf(p0x, p1x), C.inv_side, xoff);
+    LinkScan K;
+    K.p0x = p0x; K.p0y = p0y; K.p1x = p1x; K.p1y = p1y; K.side = C.side; K.have_link = false; K.result = 0;
+    const uint32_t *rowp = V.bits + r_lo * G.wpr;
+    const bool steep = (r_hi - r_lo >= 2) && (fabsf(dy) * 64.0f >= fabsf(dx));
+    if (!steep) {
+        // few rows, or a shallow link: every row gets the link's whole column range
+        const int c_lo = max(round_magic(useg_lo - mcell), 0), c_hi = min(round_magic(useg_hi + mcell), S1);
+        if (c_lo > c_hi) return 0;
+        for (int r = r_lo; r <= r_hi; ++r, rowp += G.wpr)
+            if (scan_row(V, rowp, r, c_lo, c_hi, K)) return 1;
+        return K.result;
     }
-    return result;
+    // Steep link: one row per iteration, the column interval follows the line incrementally.  In cell units
+    // u(y) = x(y)*inv_side + xoff is linear in y with du = -s per row (s = dx/dy; a row is one cell high), so the
+    // bottom edge of row r has u = u0 - (r - r_lo)*s (one FMA, no accumulation) and its top edge is the previous
+    // row's bottom edge.  The interval is widened by mm cells -- mcell of slack in y costs |s|*mcell in u, plus the
+    // float32 error of s and u0 (<= 5e-5*inv_side) -- and clamped to the link's own column range.
+    const float s = dx * __frcp_rn(dy);
+    const float mm = mcell + 5.0e-5f * C.inv_side + fabsf(s) * mcell;
+    const float clamp_lo = useg_lo - mm, clamp_hi = useg_hi + mm;
+    const float yb0 = C.half - (float)r_lo * C.side;                          // bottom edge of row r_lo
+    const float u0 = fmaf(fmaf(yb0 - p0y, s, p0x), C.inv_side, xoff);
+    float uprev = u0 + s, k = 0.0f;                                           // top edge of row r_lo
+    for (int r = r_lo; r <= r_hi; ++r, rowp += G.wpr, k += 1.0f) {
+        const float ucur = fmaf(k, -s, u0);
+        const float lo = fmaxf(fminf(uprev, ucur) - mm, clamp_lo), hi = fminf(fmaxf(uprev, ucur) + mm, clamp_hi);
+        uprev = ucur;
+        const int c_lo = max(round_magic(lo), 0), c_hi = min(round_magic(hi), S1);
+        if (c_lo > c_hi) continue;
+        if (scan_row(V, rowp, r, c_lo, c_hi, K)) return 1;
+    }
+    return K.result;
 }
 
 // broad-phase selection: a compile-time choice for the rollout kernel (keeps its register
