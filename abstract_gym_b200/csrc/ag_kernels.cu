@@ -576,8 +576,11 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
 // so the expensive part (FK + traversal + narrow phase) is executed by all 32 lanes together whatever their
 // mode.  Lanes drift apart in t, so action loads / record stores are per-lane (sector-granular); this path
 // is bound by the traversal (thousands of instructions per check), not by memory.
+#ifndef AG_ASYNC_BLOCKS_PER_SM
+#define AG_ASYNC_BLOCKS_PER_SM 2
+#endif
 template <int BP, bool HAS_ACT, bool HAS_RESET_U, bool RECORD>
-__global__ void __launch_bounds__(AG_BLOCK, 2)
+__global__ void __launch_bounds__(AG_BLOCK, AG_ASYNC_BLOCKS_PER_SM)
 k_rollout_async(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G, const __grid_constant__ FastConst C,
                 const __grid_constant__ RolloutDev A) {
     extern __shared__ __align__(16) unsigned char smem[];
