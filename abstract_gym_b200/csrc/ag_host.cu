@@ -169,8 +169,9 @@ ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g,
                                     (size_t)K, cudaMemcpyDeviceToHost, cs));
             AG_CU(cudaMemcpy2DAsync(a->rec_j2 + c0, (size_t)n * 4, pl->d_j2[s], (size_t)pl->chunk * 4, (size_t)cn * 4,
                                     (size_t)K, cudaMemcpyDeviceToHost, cs));
-            AG_CU(cudaMemcpy2DAsync(a->rec_reward + c0, (size_t)n * 4, pl->d_rw[s], (size_t)pl->chunk * 4,
-                                    (size_t)cn * 4, (size_t)K, cudaMemcpyDeviceToHost, cs));
+            if (a->rec_reward)   // optional on the host side: reward is a function of flags (DESIGN.md "compact records")
+                AG_CU(cudaMemcpy2DAsync(a->rec_reward + c0, (size_t)n * 4, pl->d_rw[s], (size_t)pl->chunk * 4,
+                                        (size_t)cn * 4, (size_t)K, cudaMemcpyDeviceToHost, cs));
             AG_CU(cudaMemcpy2DAsync(a->rec_flags + c0, (size_t)n, pl->d_fl[s], (size_t)pl->chunk, (size_t)cn,
                                     (size_t)K, cudaMemcpyDeviceToHost, cs));
         }

@@ -48,7 +48,12 @@ class Trajectories:
         def host(x):
             return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
         a = host(actions)
-        return cls(host(rec["j1"]), host(rec["j2"]), a[:, :, 0], a[:, :, 1], host(rec["reward"]), host(rec["flags"]))
+        fl = host(rec["flags"])
+        if rec.get("reward") is not None:
+            rw = host(rec["reward"])
+        else:                                       # compact records: reward is a function of the flags
+            rw = np.where(fl & FLAG_DONE, np.float32(1e4), np.where(fl & FLAG_COLLISION, np.float32(-1e3), np.float32(0)))
+        return cls(host(rec["j1"]), host(rec["j2"]), a[:, :, 0], a[:, :, 1], rw, fl)
 
     @classmethod
     def concatenate(cls, parts):

@@ -215,17 +215,32 @@ class BatchedScene:
         a.step_ctr, a.reset_ctr, a.ep_len = self.step_ctr.data_ptr(), self.reset_ctr.data_ptr(), self.ep_len.data_ptr()
         if rec is not None:
             a.rec_j1, a.rec_j2 = rec["j1"].data_ptr(), rec["j2"].data_ptr()
-            a.rec_reward, a.rec_flags = rec["reward"].data_ptr(), rec["flags"].data_ptr()
+            a.rec_reward = rec["reward"].data_ptr() if rec.get("reward") is not None else None
+            a.rec_flags = rec["flags"].data_ptr()
         a.stats = self.stats.data_ptr()
         a.diag = self.diag.data_ptr()
         return a
 
-    def alloc_records(self, K, pinned_host=False):
+    def alloc_records(self, K, pinned_host=False, reward=True):
+        """Record buffers of a K-step rollout.  reward=False (host buffers only) leaves the reward plane out: in a
+        rollout record the reward is a function of the flags (`reward_from_flags`), so it need not cross PCIe."""
         kw = dict(device="cpu", pin_memory=True) if pinned_host else dict(device=self.device)
-        return dict(j1=torch.empty(K, self.n, dtype=torch.float32, **kw),
-                    j2=torch.empty(K, self.n, dtype=torch.float32, **kw),
-                    reward=torch.empty(K, self.n, dtype=torch.float32, **kw),
-                    flags=torch.empty(K, self.n, dtype=torch.uint8, **kw))
+        rec = dict(j1=torch.empty(K, self.n, dtype=torch.float32, **kw),
+                   j2=torch.empty(K, self.n, dtype=torch.float32, **kw),
+                   flags=torch.empty(K, self.n, dtype=torch.uint8, **kw))
+        if reward or not pinned_host:
+            rec["reward"] = torch.empty(K, self.n, dtype=torch.float32, **kw)
+        return rec
+
+    def reward_from_flags(self, flags):
+        """step_reward of rollout records from their flags (scene_0.py:95-100; the rollout loop resets after every
+        terminal step, so nothing is sticky): 1e4 if done, else -1e3 if collision, else 0."""
+        p = self.params()
+        f = torch.as_tensor(flags)
+        out = torch.zeros(f.shape, dtype=torch.float32, device=f.device)
+        out[(f & _lib.FLAG_COLLISION) != 0] = float(p.reward_collision)
+        out[(f & _lib.FLAG_DONE) != 0] = float(p.reward_reach)
+        return out
 
     def rollout(self, K, actions=None, reset_u=None, record=True, out=None, engine=None):
         """The loop body of experiment/experiment_0.py:20-34, K times, in ONE kernel:

@@ -298,6 +298,21 @@ def run_ours(args, rank, world, local):
                "d2h_bytes_per_step": (K * n * 13 if record else 0) + 8 * 8 * 3,
                "reps": reps, "ms_per_step": 1e3 * dt / reps,
                "api": "BatchedScene.rollout_host -> ag_rollout_host (pinned host buffers, 3-stream chunk pipeline)"}
+        if record:   # same call with compact records (no reward plane: it is a function of the flags), reported beside it
+            hout_c = {k: v for k, v in hout.items() if k != "reward"}
+            scene.rollout_host(K, hact, hout_c)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                scene.rollout_host(K, hact, hout_c)
+            barrier()
+            dtc = time.perf_counter() - t0
+            ttc = torch.tensor([dtc], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ttc, op=dist.ReduceOp.MAX)
+            e2e["compact_records"] = {"value": world * n * K * reps / float(ttc.item()), "unit": "env-steps/s",
+                                      "d2h_bytes_per_step": K * n * 9 + 8 * 8 * 3,
+                                      "note": "reward plane not copied: reward = f(flags) in a rollout record"}
     clocks = sampler.stop(wall_load0, time.time()) if sampler else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed launches + e2e loop (the timed launches alone last %.1f ms)" % total_ms

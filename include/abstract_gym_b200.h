@@ -222,7 +222,9 @@ AG_API ag_status ag_pipeline_create(ag_pipeline **out, int32_t device, int64_t n
 AG_API void ag_pipeline_destroy(ag_pipeline *pl);
 /* Same as ag_rollout but actions / rec_* / stats_host are HOST pointers (pinned for full speed);
  * env state pointers inside `a` stay DEVICE pointers (the state lives in HBM between calls).
- * Returns after all records and stats are on the host. */
+ * a->rec_reward may be NULL while the other three record pointers are set ("compact records": the reward of a
+ * rollout record is a function of its flags -- reward_reach if done, else reward_collision if collision, else 0 --
+ * so it need not cross PCIe).  Returns after all records and stats are on the host. */
 AG_API ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g,
                           const ag_rollout_args *a, int64_t *stats_host);
 

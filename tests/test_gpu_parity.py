@@ -607,3 +607,22 @@ def test_torch_custom_ops_equal_object_api(ag, torch_):
     with pytest.raises(RuntimeError):
         torch_.ops.abstract_gym_b200.collision_check(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1.cpu(),
                                                      sc.robot.joint_2, hit, 0, 1)
+
+
+@pytest.mark.gpu
+def test_rollout_host_compact_records(ag, torch_):
+    """rollout_host without the reward plane: same j1 / j2 / flags, and reward_from_flags reproduces the plane"""
+    n, K = 4096, 16
+    rng = np.random.default_rng(51)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = torch_.as_tensor(((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32)).pin_memory()
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    a, b = make_scene(ag, torch_, g, j1, j2, seed=4), make_scene(ag, torch_, g, j1, j2, seed=4)
+    full, compact = a.alloc_records(K, pinned_host=True), b.alloc_records(K, pinned_host=True, reward=False)
+    assert "reward" not in compact
+    a.rollout_host(K, acts, full, chunk_envs=1024); b.rollout_host(K, acts, compact, chunk_envs=1024)
+    for k in ("j1", "j2", "flags"):
+        assert torch_.equal(full[k], compact[k])
+    assert torch_.equal(b.reward_from_flags(compact["flags"]), full["reward"]) and int((full["flags"] != 0).sum()) > 5
+    from abstract_gym_b200.experiment.experiment_0 import Trajectories
+    assert np.array_equal(Trajectories.from_rollout(compact, acts).reward, full["reward"].numpy())
