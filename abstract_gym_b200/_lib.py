@@ -80,7 +80,7 @@ SYMBOLS = {
                         _vp, _i64, _i64, _i32, _vp]),
     "ag_rollout": (_i32, [C.POINTER(Params), C.POINTER(Grid), C.POINTER(RolloutArgs), _vp]),
     "ag_launch_count": (_i64, []),
-    "ag_pipeline_create": (_i32, [C.POINTER(_vp), _i32, _i64, _i32, _i64, _i32]),
+    "ag_pipeline_create": (_i32, [C.POINTER(_vp), _i32, _i64, _i32, _i64, _i32, _i32]),
     "ag_pipeline_destroy": (None, [_vp]),
     "ag_rollout_host": (_i32, [_vp, C.POINTER(Params), C.POINTER(Grid), C.POINTER(RolloutArgs), _vp]),
 }

@@ -83,7 +83,9 @@ struct ag_pipeline {
     int device;
     int64_t n, chunk;
     int K, record;
+    int chunk_steps;       // > 0: slice the rollout over STEPS (contiguous copies), else over envs
     cudaStream_t st[NSTAGE];
+    cudaEvent_t ev[NSTAGE];
     float *d_act[NSTAGE];
     float *d_j1[NSTAGE], *d_j2[NSTAGE], *d_rw[NSTAGE];
     uint8_t *d_fl[NSTAGE];
@@ -94,19 +96,21 @@ struct ag_pipeline {
 #define AG_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (ag_status)e_; } while (0)
 
 ag_status ag_pipeline_create(ag_pipeline **out, int32_t device, int64_t n, int32_t K, int64_t chunk_envs,
-                             int32_t record) {
+                             int32_t chunk_steps, int32_t record) {
     if (!out) return AG_ERR_NULL;
-    if (n < 1 || K < 1 || chunk_envs < 1) return AG_ERR_SHAPE;
+    if (n < 1 || K < 1 || (chunk_steps <= 0 && chunk_envs < 1)) return AG_ERR_SHAPE;
     AG_CU(cudaSetDevice(device));
     ag_pipeline *pl = new (std::nothrow) ag_pipeline();
     if (!pl) return (ag_status)cudaErrorMemoryAllocation;
     std::memset(pl, 0, sizeof(*pl));
     pl->device = device; pl->n = n; pl->K = K; pl->record = record;
+    pl->chunk_steps = chunk_steps > 0 ? (chunk_steps < K ? chunk_steps : K) : 0;
     pl->chunk = chunk_envs < n ? chunk_envs : n;
     pl->chunk = (pl->chunk + 255) & ~(int64_t)255;     // block-aligned chunks keep env->grid maps uniform
-    const size_t ck = (size_t)pl->chunk * K;
+    const size_t ck = pl->chunk_steps > 0 ? (size_t)n * pl->chunk_steps : (size_t)pl->chunk * K;
     for (int s = 0; s < ag_pipeline::NSTAGE; ++s) {
         AG_CU(cudaStreamCreateWithFlags(&pl->st[s], cudaStreamNonBlocking));
+        AG_CU(cudaEventCreateWithFlags(&pl->ev[s], cudaEventDisableTiming));
         AG_CU(cudaMalloc(&pl->d_act[s], ck * 2 * sizeof(float)));
         if (record) {
             AG_CU(cudaMalloc(&pl->d_j1[s], ck * sizeof(float)));
@@ -126,6 +130,7 @@ void ag_pipeline_destroy(ag_pipeline *pl) {
     cudaSetDevice(pl->device);
     for (int s = 0; s < ag_pipeline::NSTAGE; ++s) {
         if (pl->st[s]) { cudaStreamSynchronize(pl->st[s]); cudaStreamDestroy(pl->st[s]); }
+        if (pl->ev[s]) cudaEventDestroy(pl->ev[s]);
         cudaFree(pl->d_act[s]); cudaFree(pl->d_j1[s]); cudaFree(pl->d_j2[s]); cudaFree(pl->d_rw[s]); cudaFree(pl->d_fl[s]);
     }
     cudaFree(pl->d_stats);
@@ -145,8 +150,39 @@ ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g,
     const int64_t n = a->n, K = a->K;
     for (int s = 0; s < ag_pipeline::NSTAGE; ++s)
         AG_CU(cudaMemsetAsync(pl->d_stats + s * AG_ST_COUNT, 0, sizeof(int64_t) * AG_ST_COUNT, pl->st[s]));
+    if (pl->chunk_steps > 0) {
+        // Slices of consecutive STEPS over all envs: every copy is one contiguous block (rows t0..t0+k of
+        // the [K][n] arrays), which PCIe moves ~7 % faster than the pitched 2-D copies of env slices.  The
+        // kernels of consecutive slices depend on each other through the env state (kernel i+1 waits for
+        // kernel i's event); copies of neighbouring slices overlap them on the other two streams.
+        int i = 0;
+        for (int64_t t0 = 0; t0 < K; t0 += pl->chunk_steps, ++i) {
+            const int s = i % ag_pipeline::NSTAGE;
+            const int64_t k = (K - t0 < pl->chunk_steps) ? K - t0 : pl->chunk_steps;
+            cudaStream_t cs = pl->st[s];
+            ag_rollout_args b = *a;
+            b.K = (int32_t)k;
+            b.stats = pl->d_stats + s * AG_ST_COUNT;
+            if (a->actions) {
+                AG_CU(cudaMemcpyAsync(pl->d_act[s], a->actions + t0 * n * 2, (size_t)k * n * 8, cudaMemcpyHostToDevice, cs));
+                b.actions = pl->d_act[s];
+            }
+            if (rec) { b.rec_j1 = pl->d_j1[s]; b.rec_j2 = pl->d_j2[s]; b.rec_reward = pl->d_rw[s]; b.rec_flags = pl->d_fl[s]; }
+            if (i > 0) AG_CU(cudaStreamWaitEvent(cs, pl->ev[(i - 1) % ag_pipeline::NSTAGE], 0));
+            ag_status st = ag_rollout_impl(p, g, &b, n, cs);
+            if (st) return st;
+            AG_CU(cudaEventRecord(pl->ev[s], cs));
+            if (rec) {
+                AG_CU(cudaMemcpyAsync(a->rec_j1 + t0 * n, pl->d_j1[s], (size_t)k * n * 4, cudaMemcpyDeviceToHost, cs));
+                AG_CU(cudaMemcpyAsync(a->rec_j2 + t0 * n, pl->d_j2[s], (size_t)k * n * 4, cudaMemcpyDeviceToHost, cs));
+                if (a->rec_reward)
+                    AG_CU(cudaMemcpyAsync(a->rec_reward + t0 * n, pl->d_rw[s], (size_t)k * n * 4, cudaMemcpyDeviceToHost, cs));
+                AG_CU(cudaMemcpyAsync(a->rec_flags + t0 * n, pl->d_fl[s], (size_t)k * n, cudaMemcpyDeviceToHost, cs));
+            }
+        }
+    }
     int i = 0;
-    for (int64_t c0 = 0; c0 < n; c0 += pl->chunk, ++i) {
+    for (int64_t c0 = 0; pl->chunk_steps <= 0 && c0 < n; c0 += pl->chunk, ++i) {
         const int s = i % ag_pipeline::NSTAGE;
         const int64_t cn = (n - c0 < pl->chunk) ? n - c0 : pl->chunk;
         cudaStream_t cs = pl->st[s];

@@ -268,17 +268,18 @@ class BatchedScene:
         _lib.check(self._lib.ag_rollout(self.params(), g, C.byref(a), stream_ptr(self.device)), "ag_rollout")
         return rec
 
-    def rollout_host(self, K, actions_host=None, out_host=None, chunk_envs=1 << 17, engine=None):
+    def rollout_host(self, K, actions_host=None, out_host=None, chunk_envs=1 << 17, engine=None, chunk_steps=0):
         """End-to-end form of `rollout` for host-resident data: actions_host [K,N,2] float32 and
         the record arrays of `out_host` (alloc_records(K, pinned_host=True)) live in (pinned) host
-        memory; H2D copy, kernel and D2H copy are pipelined over env chunks on three streams.
+        memory; H2D copy, kernel and D2H copy are pipelined on three streams, over slices of `chunk_steps` steps
+        (all envs; contiguous copies, the faster form) or, with chunk_steps=0, over slices of `chunk_envs` envs.
         Returns the episode statistics of this call as a dict (also added to self.stats)."""
         record = out_host is not None
-        key = (K, int(chunk_envs), record)
+        key = (K, int(chunk_envs), int(chunk_steps), record)
         if key not in self._pipelines:
             h = C.c_void_p()
             _lib.check(self._lib.ag_pipeline_create(C.byref(h), self.device.index, self.n, K, int(chunk_envs),
-                                                    1 if record else 0), "ag_pipeline_create")
+                                                    int(chunk_steps), 1 if record else 0), "ag_pipeline_create")
             self._pipelines[key] = h
         if actions_host is not None:
             if actions_host.dtype != torch.float32 or tuple(actions_host.shape) != (K, self.n, 2) \

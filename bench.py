@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--grid", default="scene0", choices=["scene0", "c4", "c5"],
                     help="scene0: manual 9x9 map (BASELINE configs[2], the default bench line); c4: one 1024x1024 "
                          "Bernoulli(0.002) map (configs[3]); c5: a distinct 256x256 Bernoulli(0.008) map per 256 envs (configs[4])")
+    ap.add_argument("--chunk-envs", type=int, default=1 << 17, help="envs per pipeline stage of the host-buffer (e2e) path")
+    ap.add_argument("--chunk-steps", type=int, default=4, help="steps per pipeline stage of the e2e path (0: slice over envs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-envs", type=int, default=1 << 17)
@@ -280,11 +282,11 @@ def run_ours(args, rank, world, local):
             hact.copy_(actions)
             hout = scene.alloc_records(K, pinned_host=True)
         reps = max(2, min(args.steps, 5))
-        scene.rollout_host(K, hact, hout)            # warm-up (allocates the staging pipeline)
+        scene.rollout_host(K, hact, hout, chunk_envs=args.chunk_envs, chunk_steps=args.chunk_steps)   # warm-up (allocates the staging pipeline)
         barrier()
         t0 = time.perf_counter()
         for _ in range(reps):
-            scene.rollout_host(K, hact, hout)        # returns after records + stats are in host memory
+            scene.rollout_host(K, hact, hout, chunk_envs=args.chunk_envs, chunk_steps=args.chunk_steps)   # returns after records + stats are in host memory
             scene.all_reduce_stats(wait=False)
         scene.global_stats()
         barrier()
@@ -297,14 +299,15 @@ def run_ours(args, rank, world, local):
                "h2d_bytes_per_step": (K * n * 8) if record else 0,
                "d2h_bytes_per_step": (K * n * 13 if record else 0) + 8 * 8 * 3,
                "reps": reps, "ms_per_step": 1e3 * dt / reps,
-               "api": "BatchedScene.rollout_host -> ag_rollout_host (pinned host buffers, 3-stream chunk pipeline)"}
+               "api": "BatchedScene.rollout_host -> ag_rollout_host (pinned host buffers, 3-stream pipeline over %s)"
+                      % ("slices of %d steps" % args.chunk_steps if args.chunk_steps > 0 else "slices of %d envs" % args.chunk_envs)}
         if record:   # same call with compact records (no reward plane: it is a function of the flags), reported beside it
             hout_c = {k: v for k, v in hout.items() if k != "reward"}
-            scene.rollout_host(K, hact, hout_c)
+            scene.rollout_host(K, hact, hout_c, chunk_envs=args.chunk_envs, chunk_steps=args.chunk_steps)
             barrier()
             t0 = time.perf_counter()
             for _ in range(reps):
-                scene.rollout_host(K, hact, hout_c)
+                scene.rollout_host(K, hact, hout_c, chunk_envs=args.chunk_envs, chunk_steps=args.chunk_steps)
             barrier()
             dtc = time.perf_counter() - t0
             ttc = torch.tensor([dtc], dtype=torch.float64, device=dev)

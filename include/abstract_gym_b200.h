@@ -216,9 +216,11 @@ AG_API int64_t ag_launch_count(void);
  * H2D(actions) -> K4 -> D2H(records) with copies overlapping compute. */
 typedef struct ag_pipeline ag_pipeline;
 
-/* n envs resident on `device`, K steps per call, records enabled or not, chunk_envs per stage. */
+/* n envs resident on `device`, K steps per call, records enabled or not.  chunk_steps > 0: the rollout is
+ * sliced over steps (all envs, chunk_steps steps per stage; contiguous copies -- the faster form); otherwise over
+ * envs (chunk_envs envs per stage, all K steps: one kernel launch per env slice). */
 AG_API ag_status ag_pipeline_create(ag_pipeline **out, int32_t device, int64_t n, int32_t K,
-                             int64_t chunk_envs, int32_t record);
+                             int64_t chunk_envs, int32_t chunk_steps, int32_t record);
 AG_API void ag_pipeline_destroy(ag_pipeline *pl);
 /* Same as ag_rollout but actions / rec_* / stats_host are HOST pointers (pinned for full speed);
  * env state pointers inside `a` stay DEVICE pointers (the state lives in HBM between calls).

@@ -626,3 +626,29 @@ def test_rollout_host_compact_records(ag, torch_):
     assert torch_.equal(b.reward_from_flags(compact["flags"]), full["reward"]) and int((full["flags"] != 0).sum()) > 5
     from abstract_gym_b200.experiment.experiment_0 import Trajectories
     assert np.array_equal(Trajectories.from_rollout(compact, acts).reward, full["reward"].numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk_steps", [1, 5, 64])
+def test_rollout_host_step_sliced_pipeline(ag, torch_, chunk_steps):
+    """the step-sliced host pipeline (contiguous copies, dependent kernels) == one device rollout, records and state;
+    also with in-kernel Philox actions / statistics only"""
+    n, K = 5000, 12
+    rng = np.random.default_rng(10)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    a = make_scene(ag, torch_, g, j1, j2, seed=4)
+    b = make_scene(ag, torch_, g, j1, j2, seed=4)
+    ra = a.rollout(K, actions=torch_.as_tensor(acts, device="cuda"))
+    hact = torch_.as_tensor(acts).pin_memory()
+    out = b.alloc_records(K, pinned_host=True)
+    st = b.rollout_host(K, hact, out, chunk_steps=chunk_steps)
+    for k in ("j1", "j2", "reward", "flags"):
+        assert np.array_equal(ra[k].cpu().numpy(), out[k].numpy()), k
+    assert np.array_equal(a.robot.joint_1.cpu().numpy(), b.robot.joint_1.cpu().numpy())
+    assert torch_.equal(a.step_ctr, b.step_ctr) and torch_.equal(a.ep_len, b.ep_len)
+    assert a.stats_dict() == b.stats_dict() == st
+    a.rollout(K, record=False); b.rollout_host(K, None, None, chunk_steps=chunk_steps)
+    assert a.stats_dict() == b.stats_dict()
+    assert np.array_equal(a.robot.joint_2.cpu().numpy(), b.robot.joint_2.cpu().numpy())
