@@ -214,6 +214,8 @@ def run_ours(args, rank, world, local):
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    from abstract_gym_b200.sharding import bind_to_gpu_numa
+    numa_bound = bind_to_gpu_numa(local) if (world > 1 and not os.environ.get("AG_NO_NUMA_BIND")) else False
     n, K = args.envs, args.rollout_steps
     record = args.mode == "record"
     lo = rank * n                                    # weak scaling: every rank owns n envs, global ids [lo, lo+n)
@@ -336,7 +338,7 @@ def run_ours(args, rank, world, local):
                      "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
                      "peak_source": peak_src, "bytes_per_env_step": b_alg, "kernel_ms": kern_ms,
                      "kernel": "k_rollout", "note": "compute-bound path: see DESIGN.md roofline section"},
-        "clocks": clocks, "episode_stats": stats, "filter_diag_rank0": scene.diag_dict(),
+        "clocks": clocks, "episode_stats": stats, "filter_diag_rank0": scene.diag_dict(), "numa_bound": numa_bound,
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)
