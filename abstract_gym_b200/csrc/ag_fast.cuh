@@ -293,23 +293,33 @@ struct LinkScan {
     int result;
 };
 
+// narrow phase over the set bits of one (already masked) word of row r; true = certain hit
+__device__ __forceinline__ bool scan_word(const GridView &V, uint32_t word, int w, int r, LinkScan &K) {
+    while (word) {
+        const int c = (w << 5) + __ffs(word) - 1;
+        word &= word - 1;
+        if (!K.have_link) { K.L = make_link_f(K.p0x, K.p0y, K.p1x, K.p1y, K.side); K.have_link = true; }
+        const float mnx = (float)V.min_x[c], mny = (float)V.min_y[r];
+        const int v = narrow_f32(K.L, mnx, mny, mnx + K.side, mny + K.side);
+        if (v == 1) return true;
+        K.result |= v;          // 0 or 2
+    }
+    return false;
+}
+
 __device__ __forceinline__ bool scan_row(const GridView &V, const uint32_t *__restrict__ rowp, int r, int c_lo, int c_hi,
                                          LinkScan &K) {
     const int w0 = c_lo >> 5, w1 = c_hi >> 5;
     const uint32_t mlo = 0xFFFFFFFFu << (c_lo & 31), mhi = 0xFFFFFFFFu >> (31 - (c_hi & 31));
+    if (w0 == w1) {                                     // the usual case: the interval sits inside one word
+        const uint32_t word = rowp[w0] & mlo & mhi;
+        return word != 0 && scan_word(V, word, w0, r, K);
+    }
     for (int w = w0; w <= w1; ++w) {
         uint32_t word = rowp[w];
         if (w == w0) word &= mlo;
         if (w == w1) word &= mhi;
-        while (word) {
-            const int c = (w << 5) + __ffs(word) - 1;
-            word &= word - 1;
-            if (!K.have_link) { K.L = make_link_f(K.p0x, K.p0y, K.p1x, K.p1y, K.side); K.have_link = true; }
-            const float mnx = (float)V.min_x[c], mny = (float)V.min_y[r];
-            const int v = narrow_f32(K.L, mnx, mny, mnx + K.side, mny + K.side);
-            if (v == 1) return true;
-            K.result |= v;          // 0 or 2
-        }
+        if (word != 0 && scan_word(V, word, w, r, K)) return true;
     }
     return false;
 }
