@@ -652,3 +652,61 @@ def test_rollout_host_step_sliced_pipeline(ag, torch_, chunk_steps):
     a.rollout(K, record=False); b.rollout_host(K, None, None, chunk_steps=chunk_steps)
     assert a.stats_dict() == b.stats_dict()
     assert np.array_equal(a.robot.joint_2.cpu().numpy(), b.robot.joint_2.cpu().numpy())
+
+
+def _compare_rollout(ag, torch, oracle, sc, st, K, actions, params, grids_sq):
+    rec, stats0 = oracle.rollout(st, K, grids_sq, seed=sc.seed, actions_f32=actions, params=params)
+    drec = sc.rollout(K, actions=torch.as_tensor(actions, device="cuda"))
+    torch.cuda.synchronize()
+    for k in ("flags", "reward", "j1", "j2"):
+        assert np.array_equal(drec[k].cpu().numpy(), rec[k]), k
+    assert np.array_equal(sc.robot.joint_1.cpu().numpy(), st.j1) and np.array_equal(sc.flags.cpu().numpy(), st.flags)
+    assert np.array_equal(sc.ep_len.cpu().numpy().view(np.uint32), st.ep_len)
+    assert np.array_equal(sc.reset_ctr.cpu().numpy().view(np.uint32), st.reset_ctr)
+    return rec, stats0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["exact", "fast"])
+def test_rollout_joint_target_mode(ag, torch_, oracle, engine):
+    """choose_j_tar (scene_0.py:123-127): done when both joints are within 2e-3 of target_j; envs start around it"""
+    n, K = 4096, 32
+    rng = np.random.default_rng(61)
+    tj = np.array([2.3, 4.1])
+    j1, j2 = tj[0] + rng.normal(0, 0.02, n), tj[1] + rng.normal(0, 0.02, n)
+    acts = ((rng.random((K, n, 2)) - 0.5) * 0.02).astype(np.float32)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    sc = make_scene(ag, torch_, g, j1, j2, engine=engine, seed=13)
+    sc.choose_j_tar, sc.target_j = True, tj
+    p = oracle.default_params()
+    p.choose_j_tar, p.target_j1, p.target_j2 = 1, tj[0], tj[1]
+    st = oracle.RolloutState(j1, j2)
+    rec, _ = _compare_rollout(ag, torch_, oracle, sc, st, K, acts, p, [oracle.manual_grid()[0]])
+    assert int(((rec["flags"] & 2) != 0).sum()) > 50                  # the target is actually reached
+    assert sc.stats_dict()["successes"] == int(((rec["flags"] & 2) != 0).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["exact", "fast"])
+def test_rollout_entered_with_sticky_state_and_huge_angles(ag, torch_, oracle, engine):
+    """a rollout entered with sticky reward / flags left by earlier step() calls (scene_0.py:95-100 never clears
+    them) records them on its first step and resets; joints beyond the float32 filter's range (|j| >= 2^20 rad) go
+    through the float64 path"""
+    n, K = 4096, 24
+    rng = np.random.default_rng(62)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    j1[::5] += 2 * np.pi * np.round(rng.uniform(2e5, 3e6, len(j1[::5])))   # same poses, many turns away
+    pre = (rng.random((3, n, 2)) - 0.5) * 0.6                               # big pre-steps: many collisions, no reset
+    acts = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    sq, ci = oracle.manual_grid()
+    sc = make_scene(ag, torch_, g, j1, j2, engine=engine, seed=14)
+    st = oracle.RolloutState(j1, j2)
+    rw = np.zeros(n); fl = np.zeros(n, dtype=np.uint8)
+    for t in range(3):
+        sc.step(torch_.as_tensor(pre[t], device="cuda"))
+        oracle.step_batch(st.j1, st.j2, pre[t], rw, fl, sq, ci)
+    assert np.array_equal(sc.flags.cpu().numpy(), fl) and 200 < int((fl != 0).sum()) < n
+    st.reward[:] = rw.astype(np.float32); st.flags[:] = fl
+    rec, _ = _compare_rollout(ag, torch_, oracle, sc, st, K, acts, oracle.default_params(), [sq])
+    assert np.array_equal(rec["flags"][0] != 0, (fl != 0) | (rec["flags"][0] != 0))   # sticky flags show on step 0
