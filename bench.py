@@ -261,12 +261,15 @@ def run_ours(args, rank, world, local):
         scene.rollout(K, actions=actions, record=record, out=rec)
         b.record()
         scene.all_reduce_stats(wait=False)
+    loop_end = torch.cuda.Event(enable_timing=True)
+    loop_end.record()
     scene.global_stats()                             # the last reduction is inside the timed region
     stop.record()
     barrier()
     wall1 = time.time()
     total_ms = start.elapsed_time(stop)
     kern_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    tail_ms = loop_end.elapsed_time(stop)            # waiting for the last statistics reductions
     launches = ag.launch_count() - launches0
     t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -339,6 +342,7 @@ def run_ours(args, rank, world, local):
                      "peak_source": peak_src, "bytes_per_env_step": b_alg, "kernel_ms": kern_ms,
                      "kernel": "k_rollout", "note": "compute-bound path: see DESIGN.md roofline section"},
         "clocks": clocks, "episode_stats": stats, "filter_diag_rank0": scene.diag_dict(), "numa_bound": numa_bound,
+        "stats_reduce_tail_ms_rank0": tail_ms,
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)
