@@ -56,24 +56,10 @@ __host__ __device__ __forceinline__ FastConst make_fast_const(const ag_params &P
     return C;
 }
 
-// sin(pi*f)/f and cos(pi*f) for f in [-0.5, 0.5] (half turns) as polynomials in u = f*f: degree-4
-// near-minimax fits (approximation error 1.4e-8 / 4.7e-8).  Evaluated in float32 the sine and cosine are
-// within 2.1e-7 of the float64 values, the link end points within 1.4e-7 m (4e6 random angles, emulated
-// op for op in numpy: DESIGN.md "FAST engine error budget"; measured on the GPU by test_fast_fk_error_budget).
-__device__ __forceinline__ void sincos_half(float f, float &s, float &c) {
-    const float u = f * f;
-    float ps = 0.07765940576791763f;
-    ps = fmaf(ps, u, -0.5982921719551086f);
-    ps = fmaf(ps, u, 2.5500776767730713f);
-    ps = fmaf(ps, u, -5.167710304260254f);
-    ps = fmaf(ps, u, 3.1415927410125732f);
-    s = ps * f;
-    float pc = 0.2196967899799347f;
-    pc = fmaf(pc, u, -1.3318802118301392f);
-    pc = fmaf(pc, u, 4.058412075042725f);
-    pc = fmaf(pc, u, -4.934792995452881f);
-    c = fmaf(pc, u, 0.9999999403953552f);
-}
+// sin(pi*f)/f and cos(pi*f) for f in [-0.5, 0.5] (half turns) are degree-4 polynomials in u = f*f, near-minimax
+// fits (approximation error 1.4e-8 / 4.7e-8).  Evaluated in float32 the sine and cosine are within 2.1e-7 of the
+// float64 values, the link end points within 1.4e-7 m (4e6 random angles, emulated op for op in numpy: DESIGN.md
+// "FAST engine"); both angles go through the same Horner chain at once (fast_forward_kinematics below).
 
 // Packed float32x2 arithmetic (Blackwell FFMA2 / FMUL2: two float32 operations per issue slot); the
 // two halves carry the two joint angles through the same polynomial.
@@ -108,7 +94,7 @@ __device__ __forceinline__ ArmF fast_forward_kinematics(double j1, double j2, co
     reduce_half_turns(j1, C.l1, f.x, sl.x);
     reduce_half_turns(j2, C.l2, f.y, sl.y);
     ok = (fabs(j1) < 1048576.0) && (fabs(j2) < 1048576.0);     // two DSETP on the (idle) FP64 pipe
-    // sincos_half() on both angles at once: same coefficients, same operation order, FFMA2
+    // both angles at once, FFMA2
     const float2 u = mul2(f, f);
     float2 ps = splat2(0.07765940576791763f);
     ps = fma2(ps, u, splat2(-0.5982921719551086f));
@@ -463,20 +449,6 @@ AG_COLD int cold_exact_decide(const ag_params &P, const GridDev &G, const GridVi
     return (hit ? 1 : 0) | (reached ? 2 : 0) | (axis << 2);
 }
 
-// The call-free float32 filter of one step: returns c | (r << 2) with c (collision) and r (target
-// reached) each 0 = certainly not, 1 = certainly, 2 = undecided (needs cold_exact_decide).
-template <int BP>
-__device__ __forceinline__ int fast_filter(const ag_params &P, const GridDev &G, const GridView &V, const FastList *fl,
-                                           const FastConst &C, double q1, double q2) {
-    bool ok;
-    const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
-    const int c = ok ? arm_fast<BP>(G, V, fl, C, a) : 2;
-    int r;
-    if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
-    else r = ok ? reach_fast(C, a) : 2;
-    return c | (r << 2);
-}
-
 // One step's two decisions for the FAST engine: bit0 collision, bit1 target reached, bits 2.. axis-aligned count.
 // want_reach=false (reset candidates, K2, K3): only the collision bit is meaningful.
 template <int BP>
@@ -492,14 +464,6 @@ __device__ __forceinline__ int fast_decide(const ag_params &P, const GridDev &G,
     }
     if (c == 2 || r == 2) return cold_exact_decide(P, G, V, fl, q1, q2, c, r);
     return c | (r << 1);
-}
-
-// out-of-line collision_check of a candidate pose for the (rare) reset path of the rollout kernel
-template <int BP>
-AG_COLD int cold_fast_collides(const ag_params &P, const GridDev &G, const GridView &V,
-                                               const FastList *fl, double q1, double q2) {
-    const FastConst C = make_fast_const(P, G);
-    return fast_decide<BP>(P, G, V, fl, C, q1, q2, false);
 }
 
 // FAST collision_check when the float64 arm is already known (K1 needs it for its outputs)

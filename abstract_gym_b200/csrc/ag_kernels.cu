@@ -167,12 +167,11 @@ __global__ void k_move_to_joint_pose(double *__restrict__ j1, double *__restrict
 }
 
 // collision_check of one pose for K2/K3 (flag only unless WANT_FIRST)
-template <int ENGINE, bool WANT_FIRST, int BP = BP_ANY, bool COLD = false>
+template <int ENGINE, bool WANT_FIRST, int BP = BP_ANY>
 __device__ __forceinline__ bool pose_collides(const ag_params &P, const GridDev &G, const BlockCtx &B,
                                               const FastConst &C, double j1, double j2, int &fh, int &axis) {
     if constexpr (ENGINE == AG_ENGINE_FAST && !WANT_FIRST) {
-        const int d = COLD ? cold_fast_collides<BP>(P, G, B.V, B.fl, j1, j2)
-                           : fast_decide<BP>(P, G, B.V, B.fl, C, j1, j2, false);
+        const int d = fast_decide<BP>(P, G, B.V, B.fl, C, j1, j2, false);
         axis += d >> 2;
         return d & 1;
     } else {
@@ -254,7 +253,7 @@ __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const Grid
 
 // shared by K3 and K4: scenario/scene_0.py:174-181 with a bound.  `colliding` is the
 // collision_check() of the current pose.
-template <int ENGINE, bool HAS_RESET_U, int BP = BP_ANY, bool COLD = false>
+template <int ENGINE, bool HAS_RESET_U, int BP = BP_ANY>
 __device__ __forceinline__ void resample_pose(const ag_params &P, const GridDev &G, const BlockCtx &B,
                                               const FastConst &C, bool colliding, double &j1, double &j2,
                                               uint32_t &rc, const double *reset_u_env, int32_t R, uint64_t seed,
@@ -276,7 +275,7 @@ __device__ __forceinline__ void resample_pose(const ag_params &P, const GridDev 
         j1 = __dmul_rn(__dmul_rn(u0, 3.141592653589793), 2.0);    // scene_0.py:180  rand()*pi*2.0
         j2 = __dmul_rn(__dmul_rn(u1, 3.141592653589793), 2.0);    // :181
         int fh = 0, axis = 0;
-        colliding = pose_collides<ENGINE, false, BP, COLD>(P, G, B, C, j1, j2, fh, axis);
+        colliding = pose_collides<ENGINE, false, BP>(P, G, B, C, j1, j2, fh, axis);
         if (axis) acc32(s_acc, AG_ST_AXIS_ALIGNED, axis);
     }
 }
@@ -403,7 +402,7 @@ __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, 
         if (d & 1) {   // Scene.reset(): the pose is unchanged since the step, so collision_check() == (d & 1)
             const int64_t e = hc->e;
             uint32_t rc = A.reset_ctr[e];
-            resample_pose<ENGINE, HAS_RESET_U, BP, false>(P, G, B, C, true, q1, q2, rc,
+            resample_pose<ENGINE, HAS_RESET_U, BP>(P, G, B, C, true, q1, q2, rc,
                                                           HAS_RESET_U ? A.reset_u + e * A.R * 2 : nullptr, A.R, A.seed,
                                                           (uint64_t)(A.env_id0 + e), s_acc);
             A.reset_ctr[e] = rc;
@@ -426,7 +425,8 @@ __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, 
 //            goes straight back into the inner loop.
 //   outer  : event lanes run the out-of-line cold_section() (the only call; registers are exchanged
 //            through HotCtx), then the warp re-enters in lockstep.
-// Engines without the obstacle list (traversal, EXACT, BRUTE) have no pre-test: every step is "slow".
+// The EXACT / BRUTE reference engines have no pre-test (every step is "slow"); the FAST engine on grids that need
+// the cell traversal runs k_rollout_async instead.
 template <int ENGINE, int BP, bool HAS_ACT, bool HAS_RESET_U, bool RECORD, bool FULL, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (ENGINE == AG_ENGINE_FAST ? (BP == BP_LIST ? AG_FAST_BLOCKS_PER_SM : 2) : 1) * (AG_BLOCK / BLOCK))
 k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G, const __grid_constant__ FastConst C,
@@ -525,10 +525,6 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                         undecided = ((c | r) & 2) != 0;
                         cr = c | (r << 2);
                         d = (c & 1) | ((r & 1) << 1);
-                    } else if constexpr (ENGINE == AG_ENGINE_FAST) {
-                        cr = fast_filter<BP>(P, G, B.V, B.fl, C, q1, q2);        // (c | r << 2), c,r in {0,1,2}
-                        undecided = ((cr | (cr >> 2)) & 2) != 0;
-                        d = (cr & 1) | ((cr >> 1) & 2);                          // -> bit0 collision, bit1 reached
                     } else {
                         d = step_decide<ENGINE, BP>(P, G, B, C, q1, q2);
                     }
