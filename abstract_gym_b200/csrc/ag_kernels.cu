@@ -331,24 +331,37 @@ __device__ __forceinline__ int step_decide(const ag_params &P, const GridDev &G,
     }
 }
 
-// Everything thread-private that the hot loop carries.  It lives in registers inside the inner
-// loops and is spilled to this struct (local memory) only around the out-of-line cold section, so
-// that no value is live across the ABI call: that is what keeps the inner loop spill-free under a
-// 64-register budget (DESIGN.md "register allocation of K4").
-struct HotCtx {
-    double q1, q2;
-    const float2 *act;       // action row of step t + AG_RING - 1: the next one to prefetch
-    const uint32_t *vbits;   // this thread's grid view
-    const double *vminx, *vminy;
-    const FastList *fl;
-    int64_t o;               // record offset of step t
-    int64_t e;               // env index within the launch
-    float rw;
-    uint32_t flags, mask;
-    int el_off;              // episode length after step t = el_off + t + 1
-    int t, d;
-    int undecided;           // 0, or 16 | c | r << 2: the float32 filter's verdicts (2 = undecided) of step t
+// Everything thread-private that the hot loop carries.  It lives in registers inside the inner loops and is
+// parked in this shared-memory block (structure of arrays: conflict-free) only around the out-of-line cold
+// section, so that no value is live across the ABI call: that is what keeps the inner loop spill-free under a
+// 64-register budget (DESIGN.md "register allocation of K4").  It used to be a struct in local memory; ncu
+// counted 37 M local-memory sectors per launch for it -- as much L2 traffic as the action and record streams.
+template <int BLOCK>
+struct HotShared {
+    double q1[BLOCK], q2[BLOCK];
+    const float2 *act[BLOCK];   // action row of step t + AG_RING - 1: the next one to prefetch
+    int64_t o[BLOCK];           // record offset of step t
+    float rw[BLOCK];
+    uint32_t flags[BLOCK];
+    int el_off[BLOCK];          // episode length after step t = el_off + t + 1
+    int t[BLOCK], d[BLOCK];
+    int undecided[BLOCK];       // 0, or 16 | c | r << 2: the float32 filter's verdicts (2 = undecided) of step t
 };
+
+// this thread's view of its grid: the block's shared-memory copy (layout of stage_grid) or global memory
+__device__ __forceinline__ GridView thread_view(const GridDev &G, unsigned char *smem, int64_t gid) {
+    GridView V;
+    if (G.stage) {
+        const int spad = (G.S + 1) & ~1;
+        V.bits = reinterpret_cast<const uint32_t *>(smem + 16);
+        V.min_x = reinterpret_cast<const double *>(smem + 16 + (uint32_t)G.stride_words * 4u);
+        V.min_y = V.min_x + spad;
+    } else {
+        V.bits = G.bits + grid_of_env(G, gid) * G.stride_words;
+        V.min_x = G.min_x; V.min_y = G.min_y;
+    }
+    return V;
+}
 
 // Action prefetch ring: every thread streams its own actions global -> shared with cp.async (LDGSTS), AG_RING - 1
 // steps ahead of their use, so that no register and no warp ever waits for a DRAM round trip (with a
@@ -376,41 +389,45 @@ __device__ __forceinline__ void store_record(const RolloutDev &A, int64_t o, dou
 
 // Cold section, out of line: (1) finish a step whose float32 filter was undecided with the
 // float64 reference arithmetic, (2) episode end (experiment_0.py:30-34): statistics + Scene.reset().
-template <int ENGINE, int BP, bool HAS_RESET_U, bool RECORD>
+template <int ENGINE, int BP, bool HAS_RESET_U, bool RECORD, int BLOCK>
 __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, const FastConst &C, const RolloutDev &A,
-                                          HotCtx *hc, unsigned long long *s_acc) {
-    double q1 = hc->q1, q2 = hc->q2;
-    float rw = hc->rw;
-    uint32_t fl = hc->flags;
-    int d = hc->d;
+                                          HotShared<BLOCK> &hs, const FastList *fl_list, unsigned long long *s_acc) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int x = threadIdx.x;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + x;
+    double q1 = hs.q1[x], q2 = hs.q2[x];
+    float rw = hs.rw[x];
+    uint32_t fl = hs.flags[x];
+    int d = hs.d[x];
+    const int t = hs.t[x], und = hs.undecided[x];
     BlockCtx B;
-    B.V.bits = hc->vbits; B.V.min_x = hc->vminx; B.V.min_y = hc->vminy; B.fl = hc->fl;
-    if (hc->undecided) {
+    B.V = thread_view(G, smem, A.env_id0 + e);
+    B.fl = fl_list;
+    if (und) {
         acc32(s_acc, AG_ST_COUNT + AG_DIAG_EXACT_STEPS, 1);
-        d = cold_exact_decide(P, G, B.V, B.fl, q1, q2, hc->undecided & 3, (hc->undecided >> 2) & 3);   // the filter's verdicts
+        d = cold_exact_decide(P, G, B.V, B.fl, q1, q2, und & 3, (und >> 2) & 3);  // the filter's verdicts
         if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
         if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
-        store_record<RECORD>(A, hc->o, q1, q2, rw, fl);                           // experiment_0.py:23-25
+        store_record<RECORD>(A, hs.o[x], q1, q2, rw, fl);                         // experiment_0.py:23-25
     }
     if (d >> 2) acc32(s_acc, AG_ST_AXIS_ALIGNED, d >> 2);
     if (fl) {                                                                     // experiment_0.py:30-34
         acc32(s_acc, AG_ST_EPISODES, 1);
         if (fl & AG_FLAG_COLLISION) acc32(s_acc, AG_ST_COLLISIONS, 1);
         if (fl & AG_FLAG_DONE) acc32(s_acc, AG_ST_SUCCESSES, 1);
-        atomicAdd(&s_acc[AG_ST_EP_LEN_SUM], (unsigned long long)(uint32_t)(hc->el_off + hc->t + 1));
+        atomicAdd(&s_acc[AG_ST_EP_LEN_SUM], (unsigned long long)(uint32_t)(hs.el_off[x] + t + 1));
         acc32(s_acc, AG_ST_RETURN_MILLI, __float2int_rn(rw * 1e-3f));
         if (d & 1) {   // Scene.reset(): the pose is unchanged since the step, so collision_check() == (d & 1)
-            const int64_t e = hc->e;
             uint32_t rc = A.reset_ctr[e];
             resample_pose<ENGINE, HAS_RESET_U, BP>(P, G, B, C, true, q1, q2, rc,
-                                                          HAS_RESET_U ? A.reset_u + e * A.R * 2 : nullptr, A.R, A.seed,
-                                                          (uint64_t)(A.env_id0 + e), s_acc);
+                                                   HAS_RESET_U ? A.reset_u + e * A.R * 2 : nullptr, A.R, A.seed,
+                                                   (uint64_t)(A.env_id0 + e), s_acc);
             A.reset_ctr[e] = rc;
         }
-        rw = 0.0f; fl = 0; hc->el_off = -(hc->t + 1);                             // scene_0.py:111-113
+        rw = 0.0f; fl = 0; hs.el_off[x] = -(t + 1);                               // scene_0.py:111-113
     }
-    hc->q1 = q1; hc->q2 = q2; hc->rw = rw; hc->flags = fl;
-    hc->t += 1; hc->o += A.row_stride;
+    hs.q1[x] = q1; hs.q2[x] = q2; hs.rw[x] = rw; hs.flags[x] = fl;
+    hs.t[x] = t + 1; hs.o[x] += A.row_stride;
 }
 
 // Three nested loops, warp-synchronous (every lane of a warp is at the same step t, so action loads and
@@ -424,7 +441,7 @@ __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, 
 //            event -- collision, target reached, undecided filter, axis-aligned evaluation -- the warp
 //            goes straight back into the inner loop.
 //   outer  : event lanes run the out-of-line cold_section() (the only call; registers are exchanged
-//            through HotCtx), then the warp re-enters in lockstep.
+//            through HotShared), then the warp re-enters in lockstep.
 // The EXACT / BRUTE reference engines have no pre-test (every step is "slow"); the FAST engine on grids that need
 // the cell traversal runs k_rollout_async instead.
 template <int ENGINE, int BP, bool HAS_ACT, bool HAS_RESET_U, bool RECORD, bool FULL, int BLOCK>
@@ -434,6 +451,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ FastList s_fl;
     __shared__ unsigned long long s_acc[AG_ST_COUNT + AG_DIAG_COUNT];
+    __shared__ HotShared<BLOCK> hs;
     __shared__ __align__(16) float2 s_ring[HAS_ACT ? AG_RING * BLOCK : 1];
     __shared__ __align__(16) float4 s_arm[(ENGINE == AG_ENGINE_FAST && BP == BP_LIST) ? BLOCK : 1];   // float32 arm of a slow lane
     if (threadIdx.x < AG_ST_COUNT + AG_DIAG_COUNT) s_acc[threadIdx.x] = 0;
@@ -442,10 +460,10 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
     constexpr bool LIST = (ENGINE == AG_ENGINE_FAST && BP == BP_LIST);
     const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e0 < A.n) {
-        HotCtx hc;
-        hc.q1 = A.j1[e0]; hc.q2 = A.j2[e0]; hc.rw = A.reward[e0]; hc.flags = A.flags[e0];
-        hc.el_off = (int)A.ep_len[e0];
-        hc.act = nullptr;
+        const int x = threadIdx.x;
+        hs.q1[x] = A.j1[e0]; hs.q2[x] = A.j2[e0]; hs.rw[x] = A.reward[e0]; hs.flags[x] = A.flags[e0];
+        hs.el_off[x] = (int)A.ep_len[e0];
+        hs.act[x] = nullptr;
         const uint32_t ring0 = smem_u32(&s_ring[HAS_ACT ? threadIdx.x : 0]);     // this thread's column of the ring
         if (HAS_ACT) {                                                           // steps 0 .. AG_RING-2 in flight
             const float2 *p = reinterpret_cast<const float2 *>(A.actions) + e0;
@@ -455,29 +473,29 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                 cp_async_commit();
                 p += A.row_stride;
             }
-            hc.act = p;
+            hs.act[x] = p;
         }
-        hc.vbits = B0.V.bits; hc.vminx = B0.V.min_x; hc.vminy = B0.V.min_y; hc.fl = B0.fl;
-        hc.o = e0; hc.e = e0; hc.mask = __activemask(); hc.t = 0; hc.d = 0; hc.undecided = 0;
+        hs.o[x] = e0; hs.t[x] = 0; hs.d[x] = 0; hs.undecided[x] = 0;
+        const uint32_t lane_mask = __activemask();
         const uint32_t sc0 = A.step_ctr[e0];
         A.step_ctr[e0] = sc0 + (uint32_t)A.K;
         const float reach_thr_clean = C.reach_eps + (AG_DELTA_P + 2.0e-7f);      // reach_fast()'s margin
         for (;;) {                                                               // ---- outer
             // hot state: struct -> registers
-            double q1 = hc.q1, q2 = hc.q2;
-            float rw = hc.rw;
-            uint32_t fl = hc.flags;
-            const uint32_t warp_mask = FULL ? 0xFFFFFFFFu : hc.mask;   // FULL: n % 32 == 0, every warp is complete
-            const float2 *act = hc.act;
-            int64_t o = hc.o;
-            int t = hc.t, d = 0, cr = 0;
+            double q1 = hs.q1[x], q2 = hs.q2[x];
+            float rw = hs.rw[x];
+            uint32_t fl = hs.flags[x];
+            const uint32_t warp_mask = FULL ? 0xFFFFFFFFu : lane_mask;   // FULL: n % 32 == 0, every warp is complete
+            const float2 *act = hs.act[x];
+            int64_t o = hs.o[x];
+            int t = hs.t[x], d = 0, cr = 0;
             bool undecided = false, event = false;
             // a lane whose sticky state is not clean (flags / reward left by earlier step() calls) is
             // forced through the slow branch: an infinite threshold makes its reach pre-test fire
             float reach_thr = ((fl != 0) | (rw != 0.0f)) ? __int_as_float(0x7f800000) : reach_thr_clean;
             BlockCtx B;
-            B.V.bits = hc.vbits; B.V.min_x = hc.vminx; B.V.min_y = hc.vminy; B.fl = LIST ? &s_fl : hc.fl;
-            const uint64_t gid = (uint64_t)(A.env_id0 + hc.e);
+            B.V = B0.V; B.fl = LIST ? &s_fl : B0.fl;
+            const uint64_t gid = (uint64_t)(A.env_id0 + e0);
             for (;;) {                                                           // ---- middle
                 bool slow = true;
 #pragma unroll 1
@@ -542,18 +560,18 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                 ++t; o += A.row_stride;
             }
             // registers -> struct
-            hc.q1 = q1; hc.q2 = q2; hc.rw = rw; hc.flags = fl;
+            hs.q1[x] = q1; hs.q2[x] = q2; hs.rw[x] = rw; hs.flags[x] = fl;
             if (t >= A.K) break;
-            hc.act = act; hc.o = o; hc.t = t; hc.d = d; hc.undecided = undecided ? (cr | 16) : 0;
+            hs.act[x] = act; hs.o[x] = o; hs.t[x] = t; hs.d[x] = d; hs.undecided[x] = undecided ? (cr | 16) : 0;
             if (event) {
                 acc32(s_acc, AG_ST_COUNT + AG_DIAG_COLD_CALLS, 1);
-                cold_section<ENGINE, BP, HAS_RESET_U, RECORD>(P, G, C, A, &hc, s_acc);
-            } else { hc.t = t + 1; hc.o = o + A.row_stride; }
+                cold_section<ENGINE, BP, HAS_RESET_U, RECORD, BLOCK>(P, G, C, A, hs, B0.fl, s_acc);
+            } else { hs.t[x] = t + 1; hs.o[x] = o + A.row_stride; }
             if ((threadIdx.x & 31) == 0) acc32(s_acc, AG_ST_COUNT + AG_DIAG_WARP_EXITS, 1);
         }
         acc32(s_acc, AG_ST_ENV_STEPS, A.K);
-        A.j1[e0] = hc.q1; A.j2[e0] = hc.q2; A.reward[e0] = hc.rw; A.flags[e0] = (uint8_t)hc.flags;
-        A.ep_len[e0] = (uint32_t)(hc.el_off + A.K);
+        A.j1[e0] = hs.q1[x]; A.j2[e0] = hs.q2[x]; A.reward[e0] = hs.rw[x]; A.flags[e0] = (uint8_t)hs.flags[x];
+        A.ep_len[e0] = (uint32_t)(hs.el_off[x] + A.K);
     }
     stats_flush(s_acc, A.stats);
     if (A.diag != nullptr && threadIdx.x < AG_DIAG_COUNT) {
