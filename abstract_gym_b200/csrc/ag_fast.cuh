@@ -137,13 +137,16 @@ __device__ __forceinline__ int narrow_f32(const LinkF &L, float min_x, float min
     const float a0 = ux0 * L.dy, a1 = ux1 * L.dy, b0 = uy0 * L.dx, b1 = uy1 * L.dx;
     const float cmax = fmaxf(a0, a1) - fminf(b0, b1), cmin = fminf(a0, a1) - fmaxf(b0, b1);
     if (!((cmax > -L.ecr) && (cmin < L.ecr))) return 0;   // the line certainly misses the open square
+    // OVL from four differences: ranges certainly disjoint => no hit, whatever the link's direction (for an exactly
+    // axis-aligned link the defined behaviour is the closed interval-overlap test, which also needs the overlap)
+    const float a_min = fminf(fminf(L.xhi - min_x, max_x - L.xlo), fminf(L.yhi - min_y, max_y - L.ylo));
+    if (!(a_min > -AG_M)) return 0;
     // A nearly axis-aligned link: the reference switches formulas at exactly dx == 0 / dy == 0 and
     // its lambda arithmetic gets noisy below |dx| ~ 1e-9; leave every such case to the EXACT engine.
     if (L.degenerate) return 2;
-    // OVL / B from eight differences
-    const float a_min = fminf(fminf(L.xhi - min_x, max_x - L.xlo), fminf(L.yhi - min_y, max_y - L.ylo));
+    // B from four more differences: segment wholly inside => no hit
     const float b_min = fminf(fminf(L.xlo - min_x, max_x - L.xhi), fminf(L.ylo - min_y, max_y - L.yhi));
-    if (!(a_min > -AG_M) || b_min > AG_M) return 0;       // ranges certainly disjoint, or segment wholly inside
+    if (b_min > AG_M) return 0;
     const bool p2_certain = (cmax > L.ecr) && (cmin < -L.ecr);
     return (p2_certain && (a_min > AG_M) && (b_min < -AG_M)) ? 1 : 2;
 }

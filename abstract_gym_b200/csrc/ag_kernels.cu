@@ -530,13 +530,37 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                 }
                 if (t >= A.K) break;
                 event = false;
+                // Narrow phase of the slow lanes, warp-cooperative when the warp is complete: a slow lane has at most
+                // 2 * AG_LIST_MAX = 16 (link, square) pairs, so lane L of the warp takes pair (link L & 1, square L >> 1)
+                // of the slow lane's stashed arm and one pass of narrow_f32 settles them all (instead of one lane
+                // looping over its candidates while 31 wait).
+                int c_coop = 0;
+                if constexpr (LIST && FULL) {
+                    uint32_t todo = __ballot_sync(0xFFFFFFFFu, slow);
+                    const int lane = threadIdx.x & 31, m2 = 2 * s_fl.m;
+                    while (todo) {                                               // warp-uniform: usually one pass
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const float4 af = s_arm[(threadIdx.x & ~31) + src];
+                        int v = 0;
+                        if (lane < m2) {
+                            const float4 q = s_fl.sq[lane >> 1];
+                            const bool second = (lane & 1) != 0;
+                            const LinkF L = make_link_f(second ? af.x : 0.0f, second ? af.y : 0.0f, second ? af.z : af.x,
+                                                        second ? af.w : af.y, C.side);
+                            v = narrow_f32(L, q.x, q.y, q.z, q.w);
+                        }
+                        const uint32_t hit = __ballot_sync(0xFFFFFFFFu, v == 1), und = __ballot_sync(0xFFFFFFFFu, v == 2);
+                        if (lane == src) c_coop = hit ? 1 : (und ? 2 : 0);
+                    }
+                }
                 if (slow) {
                     if constexpr (LIST) {
                         const float4 af = s_arm[threadIdx.x];                    // stashed by this lane in the inner loop
                         ArmF a;                                                  // (keeping it in registers costs spills there)
                         a.ex = af.x; a.ey = af.y; a.gx = af.z; a.gy = af.w;
                         const bool ok = (af.z == af.z);                          // NaN marks angles outside the filter's range
-                        const int c = (ok && s_fl.m >= 0) ? arm_fast_list(&s_fl, a, C) : 2;
+                        const int c = (ok && s_fl.m >= 0) ? (FULL ? c_coop : arm_fast_list(&s_fl, a, C)) : 2;
                         int r;
                         if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
                         else r = ok ? reach_fast(C, a) : 2;
