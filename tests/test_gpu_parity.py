@@ -710,3 +710,26 @@ def test_rollout_entered_with_sticky_state_and_huge_angles(ag, torch_, oracle, e
     st.reward[:] = rw.astype(np.float32); st.flags[:] = fl
     rec, _ = _compare_rollout(ag, torch_, oracle, sc, st, K, acts, oracle.default_params(), [sq])
     assert np.array_equal(rec["flags"][0] != 0, (fl != 0) | (rec["flags"][0] != 0))   # sticky flags show on step 0
+
+
+@pytest.mark.gpu
+def test_rollout_full_size_config3_vs_oracle(ag, torch_, oracle):
+    """BASELINE config 3 at its full size -- 2^20 envs x 64 fused steps, scene_0 map, FAST engine, trajectory
+    records -- against the CPU oracle on the same scripted actions: every flag, reward and recorded joint of the
+    6.7e7 env-steps bit-exact, final state and episode counters equal (the oracle needs a few seconds on the host)."""
+    n, K = 1 << 20, 64
+    rng = np.random.default_rng(2026)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = ((rng.random((K, n, 2), dtype=np.float32) - np.float32(0.5)) * np.float32(0.1))
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    sc = make_scene(ag, torch_, g, j1, j2, engine="fast", seed=77)
+    st = oracle.RolloutState(j1, j2)
+    rec, stats = oracle.rollout(st, K, [oracle.manual_grid()[0]], seed=77, actions_f32=acts)
+    drec = sc.rollout(K, actions=torch_.as_tensor(acts, device="cuda"))
+    torch_.cuda.synchronize()
+    for k in ("flags", "reward", "j1", "j2"):
+        assert np.array_equal(drec[k].cpu().numpy(), rec[k]), k
+    assert np.array_equal(sc.robot.joint_1.cpu().numpy(), st.j1) and np.array_equal(sc.robot.joint_2.cpu().numpy(), st.j2)
+    assert np.array_equal(sc.reset_ctr.cpu().numpy().view(np.uint32), st.reset_ctr)
+    assert np.array_equal(sc.stats.cpu().numpy(), stats)
+    assert stats[oracle.ST_ENV_STEPS] == n * K and stats[oracle.ST_EPISODES] > 50000 and stats[oracle.ST_SUCCESSES] > 100
