@@ -44,7 +44,7 @@ class Grid(C.Structure):
     _fields_ = [("bits", C.c_void_p), ("min_x", C.c_void_p), ("min_y", C.c_void_p),
                 ("side", C.c_double), ("env_size", C.c_double),
                 ("S", C.c_int32), ("words_per_row", C.c_int32), ("n_grids", C.c_int32), ("max_occupied", C.c_int32),
-                ("grid_stride_words", C.c_int64), ("envs_per_grid", C.c_int64)]
+                ("grid_stride_words", C.c_int64), ("envs_per_grid", C.c_int64), ("bits_t", C.c_void_p)]
 
 
 class RolloutArgs(C.Structure):

@@ -14,6 +14,7 @@ namespace agd {
 // ---------------------------------------------------------------- kernel-side grid descriptor
 struct GridDev {
     const uint32_t *bits;
+    const uint32_t *bits_t;   // transposed copy (lines = columns) or nullptr
     const double *min_x;
     const double *min_y;
     double side;       // E/(S-1)
@@ -31,6 +32,7 @@ struct GridDev {
 // what one thread sees: either shared-memory copies or global pointers
 struct GridView {
     const uint32_t *bits;
+    const uint32_t *bits_t;   // nullptr when the grid has no transposed copy
     const double *min_x;
     const double *min_y;
 };
@@ -248,50 +250,53 @@ __device__ __forceinline__ bool target_reached(const ag_params &P, double j1, do
 // ---------------------------------------------------------------- shared-memory staging of the grid
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Block-cooperative copy of `bytes` (multiple of 16, 16-byte aligned both sides) with one bulk
-// TMA transaction (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier.
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *mbar) {
-    if (threadIdx.x == 0) {
-        const uint32_t b = smem_u32(mbar);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b) : "memory");
-    }
-    __syncthreads();   // the barrier is initialised before anyone polls it
-    const uint32_t b = smem_u32(mbar);
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(b) : "memory");
-    }
-}
-
 // Stage this block's grid (bits + corner tables) into dynamic shared memory.  Layout:
-//   [mbarrier 16 B][bits: stride_words*4 B][min_x: Spad*8][min_y: Spad*8]
+//   [mbarrier 16 B][bits: stride_words*4 B][bits_t: the same, if present][min_x: Spad*8][min_y: Spad*8]
 __device__ __forceinline__ GridView stage_grid(const GridDev &G, int64_t block_gid0, unsigned char *smem) {
     GridView V;
     const int64_t g = grid_of_env(G, block_gid0);
     const uint32_t *gbits = G.bits + g * G.stride_words;
+    const uint32_t *gbits_t = G.bits_t ? G.bits_t + g * G.stride_words : nullptr;
     if (!G.stage) {
-        V.bits = gbits; V.min_x = G.min_x; V.min_y = G.min_y;
+        V.bits = gbits; V.bits_t = gbits_t; V.min_x = G.min_x; V.min_y = G.min_y;
         return V;
     }
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     uint32_t *sbits = reinterpret_cast<uint32_t *>(smem + 16);
     const uint32_t bit_bytes = (uint32_t)G.stride_words * 4u;
+    const uint32_t all_bytes = G.bits_t ? 2u * bit_bytes : bit_bytes;
     const int spad = (G.S + 1) & ~1;
-    double *sx = reinterpret_cast<double *>(smem + 16 + bit_bytes);
+    double *sx = reinterpret_cast<double *>(smem + 16 + all_bytes);
     double *sy = sx + spad;
     if (bit_bytes >= 2048u) {
-        bulk_copy_g2s(sbits, gbits, bit_bytes, mbar);
+        // one mbarrier, one expected byte count, one or two bulk copies (row-major and transposed bits)
+        if (threadIdx.x == 0) {
+            const uint32_t b = smem_u32(mbar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(all_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sbits)), "l"(gbits), "r"(bit_bytes), "r"(b) : "memory");
+            if (gbits_t)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(sbits) + bit_bytes), "l"(gbits_t), "r"(bit_bytes), "r"(b) : "memory");
+        }
+        __syncthreads();   // the barrier is initialised before anyone polls it
+        const uint32_t b = smem_u32(mbar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(b) : "memory");
+        }
     } else {
-        for (uint32_t i = threadIdx.x; i < (uint32_t)G.stride_words; i += blockDim.x) sbits[i] = gbits[i];
+        for (uint32_t i = threadIdx.x; i < (uint32_t)G.stride_words; i += blockDim.x) {
+            sbits[i] = gbits[i];
+            if (gbits_t) sbits[G.stride_words + i] = gbits_t[i];
+        }
     }
     for (int i = threadIdx.x; i < G.S; i += blockDim.x) { sx[i] = G.min_x[i]; sy[i] = G.min_y[i]; }
     __syncthreads();
-    V.bits = sbits; V.min_x = sx; V.min_y = sy;
+    V.bits = sbits; V.bits_t = G.bits_t ? sbits + G.stride_words : nullptr; V.min_x = sx; V.min_y = sy;
     return V;
 }
 

@@ -55,7 +55,9 @@ __device__ __forceinline__ BlockCtx block_prologue(const GridDev &G, int64_t env
             B.fl = s_fl;
         }
     } else {
-        B.V.bits = G.bits + grid_of_env(G, env_id0 + min(e, n - 1)) * G.stride_words;
+        const int64_t off = grid_of_env(G, env_id0 + min(e, n - 1)) * G.stride_words;
+        B.V.bits = G.bits + off;
+        B.V.bits_t = G.bits_t ? G.bits_t + off : nullptr;
         B.V.min_x = G.min_x; B.V.min_y = G.min_y;
     }
     return B;
@@ -353,11 +355,15 @@ __device__ __forceinline__ GridView thread_view(const GridDev &G, unsigned char 
     GridView V;
     if (G.stage) {
         const int spad = (G.S + 1) & ~1;
+        const uint32_t bit_bytes = (uint32_t)G.stride_words * 4u;
         V.bits = reinterpret_cast<const uint32_t *>(smem + 16);
-        V.min_x = reinterpret_cast<const double *>(smem + 16 + (uint32_t)G.stride_words * 4u);
+        V.bits_t = G.bits_t ? V.bits + G.stride_words : nullptr;
+        V.min_x = reinterpret_cast<const double *>(smem + 16 + (G.bits_t ? 2u * bit_bytes : bit_bytes));
         V.min_y = V.min_x + spad;
     } else {
-        V.bits = G.bits + grid_of_env(G, gid) * G.stride_words;
+        const int64_t off = grid_of_env(G, gid) * G.stride_words;
+        V.bits = G.bits + off;
+        V.bits_t = G.bits_t ? G.bits_t + off : nullptr;
         V.min_x = G.min_x; V.min_y = G.min_y;
     }
     return V;
@@ -724,15 +730,15 @@ ag_status make_grid_dev(const ag_params *p, const ag_grid *g, int64_t env_id0, i
         !(p->link_1 > 0 && p->link_2 > 0 && p->link_1 <= 1.0 && p->link_2 <= 1.0 && g->env_size <= 4.0))
         return AG_ERR_MODE;
     GridDev d;
-    d.bits = g->bits; d.min_x = g->min_x; d.min_y = g->min_y;
+    d.bits = g->bits; d.bits_t = g->bits_t; d.min_x = g->min_x; d.min_y = g->min_y;
     d.side = g->side; d.half = g->env_size / 2.0; d.inv_side = 1.0 / g->side;
     d.margin = 1e-9 * g->env_size;
     d.S = g->S; d.wpr = g->words_per_row; d.n_grids = g->n_grids;
     d.stride_words = g->grid_stride_words; d.envs_per_grid = g->envs_per_grid;
     const int spad = (g->S + 1) & ~1;
-    const size_t bytes = 16 + (size_t)g->grid_stride_words * 4 + (size_t)spad * 16;
+    const size_t bytes = 16 + (size_t)g->grid_stride_words * 4 * (g->bits_t ? 2 : 1) + (size_t)spad * 16;
     const bool uniform = g->n_grids == 1 || (g->envs_per_grid % AG_BLOCK == 0 && env_id0 % AG_BLOCK == 0);
-    const bool aligned = ((uintptr_t)g->bits % 16 == 0) && (g->grid_stride_words % 4 == 0);
+    const bool aligned = ((uintptr_t)g->bits % 16 == 0) && ((uintptr_t)g->bits_t % 16 == 0) && (g->grid_stride_words % 4 == 0);
     d.stage = (uniform && aligned && bytes <= (size_t)stage_max_bytes()) ? 1 : 0;
     *smem_bytes = d.stage ? bytes : 0;
     *out = d;

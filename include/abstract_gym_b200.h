@@ -79,6 +79,10 @@ typedef struct ag_grid {
     int32_t max_occupied;            /* upper bound on occupied cells of any grid; < 0 = unknown (hint only) */
     int64_t grid_stride_words;       /* >= S*words_per_row, multiple of 4 (16-byte rows for bulk copies) */
     int64_t envs_per_grid;
+    const uint32_t *bits_t;          /* optional transposed copy (same strides): bit r%32 of word
+                                      * bits_t[g*grid_stride_words + c*words_per_row + r/32] is cell (row r, col c), i.e.
+                                      * ag_grid_pack of the transposed matrices; NULL = none.  With it the FAST engine walks
+                                      * a link along its minor axis (columns for shallow links) instead of always by rows. */
 } ag_grid;
 
 /* Collision engine selection. All three return identical flags (tests/test_gpu_parity.py):
