@@ -733,3 +733,36 @@ def test_rollout_full_size_config3_vs_oracle(ag, torch_, oracle):
     assert np.array_equal(sc.reset_ctr.cpu().numpy().view(np.uint32), st.reset_ctr)
     assert np.array_equal(sc.stats.cpu().numpy(), stats)
     assert stats[oracle.ST_ENV_STEPS] == n * K and stats[oracle.ST_EPISODES] > 50000 and stats[oracle.ST_SUCCESSES] > 100
+
+
+@pytest.mark.gpu
+def test_integration_md_ctypes_stub_runs(ag, torch_):
+    """the reference-side ctypes stub printed in INTEGRATION.md is executable as written (struct layouts match the
+    header) and steps a batch exactly like BatchedScene.step"""
+    import re
+    from abstract_gym_b200 import _lib
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "INTEGRATION.md")).read()
+    m = re.search(r"```python\n(# abstract_gym/scenario/scene_0_b200\.py.*?)```", text, re.S)
+    assert m, "stub not found in INTEGRATION.md"
+    code = m.group(1).replace('C.CDLL("libabstract_gym_b200.so")', "C.CDLL(%r)" % _lib.lib_path())
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    env = ag.OccupancyGrid(size=9, random_obstacle=False)         # has .occ and .environment_size like the reference's
+    grid, keep = ns["pack_grid"](env)
+    n = 2048
+    rng = np.random.default_rng(71)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = (rng.random((n, 2)) - 0.5) * 0.6
+    ref = make_scene(ag, torch_, env, j1, j2, engine="fast")
+    ref.step(torch_.as_tensor(acts, device="cuda"))
+
+    class _S:                                                     # what the stub reads from a reference Scene
+        robot = ag.TwoJointRobot(0.0, 0.0)
+        target_c = ag.Point(-0.2, -0.3)
+    t = lambda a, dt: torch_.as_tensor(a, device="cuda").to(dt).contiguous()
+    d1, d2 = t(j1, torch_.float64), t(j2, torch_.float64)
+    rw, fl = torch_.zeros(n, dtype=torch_.float32, device="cuda"), torch_.zeros(n, dtype=torch_.uint8, device="cuda")
+    ns["step_batch"](_S, grid, d1, d2, t(acts, torch_.float64), rw, fl)
+    torch_.cuda.synchronize()
+    assert torch_.equal(d1, ref.robot.joint_1) and torch_.equal(fl, ref.flags) and torch_.equal(rw, ref.step_reward)
+    assert int((fl != 0).sum()) > 100
