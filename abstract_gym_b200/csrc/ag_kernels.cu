@@ -32,6 +32,7 @@ struct RolloutDev {
     uint8_t *rec_flags;
     unsigned long long *stats;
     unsigned long long *diag;
+    int32_t zfill;            // 1: the reward / flags planes of this launch are zero-filled up front by each warp
 };
 
 // ------------------------------------------------------------------------- per-block context
@@ -393,6 +394,34 @@ __device__ __forceinline__ void store_record(const RolloutDev &A, int64_t o, dou
     }
 }
 
+// The record of an UNEVENTFUL step has reward 0 and flags 0.  When the launch qualifies (complete warps, 16-byte
+// aligned rows) every warp zero-fills its slice of those two planes once, with warp-wide 16-byte stores (20 stores
+// for 64 steps), and the hot loop stores the two joints only; eventful steps rewrite all four fields.
+template <bool RECORD>
+__device__ __forceinline__ void store_uneventful(const RolloutDev &A, int64_t o, double q1, double q2) {
+    if (RECORD) {
+        __stcs(A.rec_j1 + o, (float)q1);
+        __stcs(A.rec_j2 + o, (float)q2);
+        if (!A.zfill) {
+            __stcs(A.rec_reward + o, 0.0f);
+            A.rec_flags[o] = 0;
+        }
+    }
+}
+
+// warp-cooperative zero fill of rows [0, K) x this warp's 32 envs of the reward (128 B per row) and flags (32 B per
+// row) planes.  warp_e0: first env of the warp (a multiple of 32).
+__device__ __forceinline__ void zero_fill_warp(const RolloutDev &A, int64_t warp_e0) {
+    const int lane = threadIdx.x & 31;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = lane >> 3; t < A.K; t += 4)            // 8 lanes x 16 B = one 128-byte row segment; 4 rows per store
+        __stcs(reinterpret_cast<float4 *>(A.rec_reward + (int64_t)t * A.row_stride + warp_e0) + (lane & 7), z4);
+    const uint4 zu = make_uint4(0u, 0u, 0u, 0u);
+    for (int t = lane >> 1; t < A.K; t += 16)           // 2 lanes x 16 B = one 32-byte row segment; 16 rows per store
+        reinterpret_cast<uint4 *>(A.rec_flags + (int64_t)t * A.row_stride + warp_e0)[lane & 1] = zu;
+    __syncwarp();                                       // orders these stores before the owners' later rewrites
+}
+
 // Cold section, out of line: (1) finish a step whose float32 filter was undecided with the
 // float64 reference arithmetic, (2) episode end (experiment_0.py:30-34): statistics + Scene.reset().
 template <int ENGINE, int BP, bool HAS_RESET_U, bool RECORD, int BLOCK>
@@ -483,6 +512,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
         }
         hs.o[x] = e0; hs.t[x] = 0; hs.d[x] = 0; hs.undecided[x] = 0;
         const uint32_t lane_mask = __activemask();
+        if (RECORD && LIST && A.zfill) zero_fill_warp(A, e0 - (threadIdx.x & 31));
         const uint32_t sc0 = A.step_ctr[e0];
         A.step_ctr[e0] = sc0 + (uint32_t)A.K;
         const float reach_thr_clean = C.reach_eps + (AG_DELTA_P + 2.0e-7f);      // reach_fast()'s margin
@@ -530,7 +560,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                         slow = !(sep >= s_fl.hm) | !(worst >= reach_thr) | !ok;             // NaN-safe: NaN is slow
                         if (P.choose_j_tar) slow |= target_reached_joint(P, q1, q2);
                         if (slow) s_arm[threadIdx.x] = make_float4(a.ex, a.ey, ok ? a.gx : __int_as_float(0x7fc00000), a.gy);
-                        store_record<RECORD>(A, o, q1, q2, 0.0f, 0u);            // an uneventful step; slow lanes rewrite theirs
+                        store_uneventful<RECORD>(A, o, q1, q2);                  // slow lanes rewrite theirs
                     }
                     if (__any_sync(warp_mask, slow)) break;
                 }
@@ -845,6 +875,9 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
     A.rec_j1 = a->rec_j1; A.rec_j2 = a->rec_j2; A.rec_reward = a->rec_reward; A.rec_flags = a->rec_flags;
     A.stats = reinterpret_cast<unsigned long long *>(a->stats);
     A.diag = reinterpret_cast<unsigned long long *>(a->diag);
+    // warp-wide 16-byte zero fill of the reward / flags record planes needs 16-byte aligned rows
+    A.zfill = (a->rec_reward != nullptr && a->n % 32 == 0 && row_stride % 16 == 0 &&
+               (uintptr_t)a->rec_reward % 16 == 0 && (uintptr_t)a->rec_flags % 16 == 0) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     // FAST engine: the obstacle-list broad phase when the caller vouches for small sparse staged grids
     // (ag_grid.max_occupied); a block whose grid turns out not to qualify falls back to EXACT per lane.
