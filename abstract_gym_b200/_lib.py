@@ -74,7 +74,7 @@ SYMBOLS = {
     "ag_inverse_kinematics": (_i32, [C.POINTER(Params), _vp, _vp, _vp, _i32, _i64, _vp]),
     "ag_move_to_joint_pose": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp]),
     "ag_collision_check": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
-    "ag_step": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+    "ag_step": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                        _i64, _i64, _i32, _vp]),
     "ag_reset": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _u64, _i32,
                         _vp, _i64, _i64, _i32, _vp]),

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const Grid
                                                    float *__restrict__ reward, uint8_t *__restrict__ flags,
                                                    double *__restrict__ ee, double *__restrict__ dist,
                                                    int32_t *__restrict__ first_hit, unsigned long long *stats,
-                                                   int64_t n, int64_t env_id0) {
+                                                   const double *__restrict__ targets, int64_t n, int64_t env_id0) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ FastList s_fl;
     __shared__ unsigned long long s_acc[AG_ST_COUNT];
@@ -219,6 +219,11 @@ __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const Grid
     __syncthreads();
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) {
+        ag_params Pe = P;                                   // per-env cartesian target (gym-style callers), if given
+        if (targets) {
+            const double2 tg = reinterpret_cast<const double2 *>(targets)[e];
+            Pe.target_x = tg.x; Pe.target_y = tg.y;
+        }
         double d1, d2;
         if (ACT_F32) {
             const float2 a = reinterpret_cast<const float2 *>(actions)[e];
@@ -241,12 +246,12 @@ __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const Grid
                 G, B.V, A, P.section_eps, fh, axis);
         }
         if (h) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }       // scene_0.py:95-97
-        if (target_reached(P, q1, q2, A)) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }   // :98-100
+        if (target_reached(Pe, q1, q2, A)) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }   // :98-100
         j1[e] = q1; j2[e] = q2; reward[e] = rw; flags[e] = fl;
         if (ee) reinterpret_cast<double2 *>(ee)[e] = make_double2(A.gx, A.gy);
         if (dist)
             reinterpret_cast<double2 *>(dist)[e] =
-                make_double2(fabs(__dsub_rn(P.target_x, A.gx)), fabs(__dsub_rn(P.target_y, A.gy)));
+                make_double2(fabs(__dsub_rn(Pe.target_x, A.gx)), fabs(__dsub_rn(Pe.target_y, A.gy)));
         if (WANT_FIRST) first_hit[e] = h ? fh : -1;
         acc32(s_acc, AG_ST_ENV_STEPS, 1);
         if (axis) acc32(s_acc, AG_ST_AXIS_ALIGNED, axis);
@@ -972,7 +977,7 @@ ag_status ag_collision_check(const ag_params *p, const ag_grid *g, const double 
 
 ag_status ag_step(const ag_params *p, const ag_grid *g, double *j1, double *j2, const void *actions,
                   int32_t actions_f32, float *reward, uint8_t *flags, double *ee, double *dist, int32_t *first_hit,
-                  int64_t *stats, int64_t n, int64_t env_id0, int32_t engine, void *stream) {
+                  int64_t *stats, const double *targets, int64_t n, int64_t env_id0, int32_t engine, void *stream) {
     if (n < 0) return AG_ERR_SHAPE;
     if (!p || !g) return AG_ERR_NULL;
     GridDev G;
@@ -981,11 +986,13 @@ ag_status ag_step(const ag_params *p, const ag_grid *g, double *j1, double *j2, 
     if (st) return st;
     if (n == 0) return AG_OK;
     if (!j1 || !j2 || !actions || !reward || !flags) return AG_ERR_NULL;
-    if (((uintptr_t)actions % (actions_f32 ? 8 : 16)) || ((uintptr_t)ee % 16) || ((uintptr_t)dist % 16)) return AG_ERR_ALIGN;
+    if (((uintptr_t)actions % (actions_f32 ? 8 : 16)) || ((uintptr_t)ee % 16) || ((uintptr_t)dist % 16) ||
+        ((uintptr_t)targets % 16))
+        return AG_ERR_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long *ust = reinterpret_cast<unsigned long long *>(stats);
 #define AG_STEP(F32, WF) { auto k = k_step<E, F32, WF>; if ((st = set_smem(k, smem))) return st; \
-        k<<<blocks_for(n), AG_BLOCK, smem, s>>>(*p, G, j1, j2, actions, reward, flags, ee, dist, first_hit, ust, n, env_id0); }
+        k<<<blocks_for(n), AG_BLOCK, smem, s>>>(*p, G, j1, j2, actions, reward, flags, ee, dist, first_hit, ust, targets, n, env_id0); }
     AG_DISPATCH_ENGINE(engine, {
         if (actions_f32) { if (first_hit) AG_STEP(true, true) else AG_STEP(true, false) }
         else             { if (first_hit) AG_STEP(false, true) else AG_STEP(false, false) }

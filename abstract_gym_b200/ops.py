@@ -102,7 +102,7 @@ def step(params: torch.Tensor, grid_bits: torch.Tensor, min_x: torch.Tensor, min
         raise RuntimeError("actions must be float32 or float64")
     _lib.check(_lib.load().ag_step(_params(params), _grid(grid_bits, min_x, min_y, grid_meta), _p(j1), _p(j2), _p(actions),
                                    1 if actions.dtype == torch.float32 else 0, _p(reward), _p(flags), None, None, None,
-                                   _p(stats), j1.numel(), env_id0, engine, stream_ptr(dev)), "ag_step")
+                                   _p(stats), None, j1.numel(), env_id0, engine, stream_ptr(dev)), "ag_step")
 
 
 @custom_op(NS + "::reset", mutates_args=("j1", "j2", "reward", "flags", "reset_ctr", "stats"))

@@ -153,21 +153,24 @@ class BatchedScene:
         return (u - 0.5) * scale_factor
 
     # ---- K1 ------------------------------------------------------------------------------------
-    def step(self, action, want_ee=False, want_first_hit=False, engine=None):
+    def step(self, action, want_ee=False, want_first_hit=False, engine=None, targets=None):
         """scene_0.py:88-103 for every env.  action: [N,2] float64 (or float32) CUDA tensor.
         Returns (joint_1, joint_2, step_reward, done, collision_status) tensors, plus a dict with
-        ee / dist / first_hit when requested."""
+        ee / dist / first_hit when requested.  targets: optional [N,2] float64 per-env cartesian targets
+        replacing target_c (gym-style callers)."""
         action = torch.as_tensor(action, device=self.device)
         if action.dtype not in (torch.float32, torch.float64):
             action = action.to(torch.float64)
         action = action.reshape(self.n, 2).contiguous()
+        if targets is not None:
+            targets = as_f64(targets, self.device).reshape(self.n, 2).contiguous()
         ee = torch.empty(self.n, 2, dtype=torch.float64, device=self.device) if want_ee else None
         dist = torch.empty(self.n, 2, dtype=torch.float64, device=self.device) if want_ee else None
         fh = torch.empty(self.n, dtype=torch.int32, device=self.device) if want_first_hit else None
         g = self.grid.c_struct()
         _lib.check(self._lib.ag_step(self.params(), g, ptr(self.robot.joint_1), ptr(self.robot.joint_2), ptr(action),
                                      1 if action.dtype == torch.float32 else 0, ptr(self.step_reward),
-                                     ptr(self.flags), ptr(ee), ptr(dist), ptr(fh), ptr(self.stats), self.n,
+                                     ptr(self.flags), ptr(ee), ptr(dist), ptr(fh), ptr(self.stats), ptr(targets), self.n,
                                      self.env_id0, self.engine if engine is None else _engine(engine),
                                      stream_ptr(self.device)), "ag_step")
         out = (self.robot.joint_1, self.robot.joint_2, self.step_reward, self.done, self.collision_status)

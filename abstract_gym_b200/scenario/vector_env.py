@@ -7,7 +7,7 @@ experiment/experiment_0.py:30-34 does.
     obs = env.reset()
     obs, reward, terminated, truncated, info = env.step(action)      # action: [N, 2] joint deltas
 
-Observation [N, 6] float64: (joint_1, joint_2, EE_x, EE_y, |target_x - EE_x|, |target_y - EE_y|) -- the two
+Observation [N, 6] float64: (joint_1, joint_2, EE_x, EE_y, |target_x - EE_x|, |target_y - EE_y|; per-env targets optional) -- the two
 quantities `check_target_reached` thresholds (scene_0.py:129-130) are the reference's only notion of goal distance.
 Every call is a fixed sequence of launches of the CUDA kernels behind the C ABI (K1 step, K3 masked reset, FK) on
 preallocated buffers, so `capture()` can record it once into a CUDA graph and `step` replays it.
@@ -23,7 +23,7 @@ from .scene_0 import BatchedScene
 
 class VectorEnv:
     def __init__(self, num_envs, env=None, device=None, seed=0, engine="fast", auto_reset=True, target_c=None,
-                 choose_j_tar=False, env_id0=0):
+                 choose_j_tar=False, env_id0=0, targets=None):
         dev = require_cuda(device)
         self.num_envs = int(num_envs)
         self.device = dev
@@ -44,8 +44,19 @@ class VectorEnv:
         self._terminated = torch.zeros(n, dtype=torch.bool, device=dev)
         self._collision = torch.zeros(n, dtype=torch.bool, device=dev)
         self._mask = torch.zeros(n, dtype=torch.uint8, device=dev)
+        # per-env cartesian targets [N,2] (None: every env uses target_c); set_targets() may change them between steps
+        self._targets = None
+        if targets is not None:
+            self._targets = torch.zeros(n, 2, dtype=torch.float64, device=dev)
+            self.set_targets(targets)
         self._graph = None
         self._lib = _lib.load()
+
+    def set_targets(self, targets):
+        """per-env cartesian targets [N,2]; written into the buffer the (possibly captured) step reads"""
+        if self._targets is None:
+            raise RuntimeError("construct VectorEnv(targets=...) to use per-env targets")
+        self._targets.copy_(torch.as_tensor(targets, dtype=torch.float64, device=self.device).reshape(self.num_envs, 2))
 
     # ---- pieces (all on preallocated buffers: capturable) ----------------------------------------
     def _observe(self, out):
@@ -55,15 +66,19 @@ class VectorEnv:
                    "ag_forward_kinematics")
         out[:, 0].copy_(sc.robot.joint_1); out[:, 1].copy_(sc.robot.joint_2)
         out[:, 2:4].copy_(self._fk[:, 2:4])
-        out[:, 4].copy_((float(sc.target_c.x) - self._fk[:, 2]).abs())
-        out[:, 5].copy_((float(sc.target_c.y) - self._fk[:, 3]).abs())
+        if self._targets is None:
+            out[:, 4].copy_((float(sc.target_c.x) - self._fk[:, 2]).abs())
+            out[:, 5].copy_((float(sc.target_c.y) - self._fk[:, 3]).abs())
+        else:
+            out[:, 4:6].copy_((self._targets - self._fk[:, 2:4]).abs())
 
     def _step_impl(self):
         sc = self.scene
         g = sc.grid.c_struct()
         _lib.check(self._lib.ag_step(sc.params(), g, ptr(sc.robot.joint_1), ptr(sc.robot.joint_2), ptr(self._action), 0,
                                      ptr(sc.step_reward), ptr(sc.flags), ptr(self._ee), ptr(self._dist), None,
-                                     ptr(sc.stats), self.num_envs, sc.env_id0, sc.engine, stream_ptr(self.device)),
+                                     ptr(sc.stats), ptr(self._targets), self.num_envs, sc.env_id0, sc.engine,
+                                     stream_ptr(self.device)),
                    "ag_step")
         self._reward.copy_(sc.step_reward)
         self._terminated.copy_(sc.flags != 0)

@@ -169,11 +169,13 @@ AG_API ag_status ag_collision_check(const ag_params *p, const ag_grid *g, const 
 
 /* K1: scenario/scene_0.py:88-103  Scene.step(action).  j1,j2,reward,flags are in/out (sticky
  * semantics).  actions: [n][2] float64 (actions_f32 == 0) or float32.  Optional outputs:
- * ee [n][2] float64 end effector, dist [n][2] float64 (|tx-EEx|, |ty-EEy|), first_hit [n] int32. */
+ * ee [n][2] float64 end effector, dist [n][2] float64 (|tx-EEx|, |ty-EEy|), first_hit [n] int32.
+ * targets: optional [n][2] float64 per-env cartesian targets replacing Scene.target_c (NULL = p->target_x/y;
+ * ignored in joint-target mode). */
 AG_API ag_status ag_step(const ag_params *p, const ag_grid *g, double *j1, double *j2, const void *actions,
                   int32_t actions_f32, float *reward, uint8_t *flags, double *ee, double *dist,
-                  int32_t *first_hit, int64_t *stats, int64_t n, int64_t env_id0, int32_t engine,
-                  void *stream);
+                  int32_t *first_hit, int64_t *stats, const double *targets, int64_t n, int64_t env_id0,
+                  int32_t engine, void *stream);
 
 /* K3: scenario/scene_0.py:105-113,174-181  Scene.reset() / random_valid_pose() for envs with
  * mask[e] != 0 (mask == NULL: all).  Candidates come from reset_u [n][R][2] float64 uniforms

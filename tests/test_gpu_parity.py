@@ -766,3 +766,36 @@ def test_integration_md_ctypes_stub_runs(ag, torch_):
     torch_.cuda.synchronize()
     assert torch_.equal(d1, ref.robot.joint_1) and torch_.equal(fl, ref.flags) and torch_.equal(rw, ref.step_reward)
     assert int((fl != 0).sum()) > 100
+
+
+@pytest.mark.gpu
+def test_per_env_targets(ag, torch_):
+    """per-env cartesian targets (gym-style callers): done fires exactly for the envs whose own target is reached,
+    goal distance is measured to the own target; VectorEnv carries them through its (captured) step"""
+    n = 2048
+    rng = np.random.default_rng(81)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = (rng.random((n, 2)) - 0.5) * 0.1
+    ee_next = ag.forward_kinematics(torch_.as_tensor(j1 + acts[:, 0], device="cuda"),
+                                    torch_.as_tensor(j2 + acts[:, 1], device="cuda"))[:, 2:4]
+    targets = ee_next.clone()
+    far = torch_.arange(n, device="cuda") % 2 == 1
+    targets[far] += 0.05                                              # odd envs: target 5 cm away in x and y
+    sc = make_scene(ag, torch_, g, j1, j2)
+    _, _, rw, done, coll, extra = sc.step(torch_.as_tensor(acts, device="cuda"), want_ee=True, targets=targets)
+    assert torch_.equal(done, ~far)
+    assert bool((rw[~far] == 1e4).all()) and bool((rw[far & ~coll] == 0).all())
+    assert float(extra["dist"][~far].max()) < 1e-12 and float((extra["dist"][far] - 0.05).abs().max()) < 1e-12
+    # VectorEnv: same targets, eager and captured
+    for graph in (False, True):
+        env = ag.VectorEnv(n, device="cuda", seed=3, targets=torch_.zeros(n, 2, dtype=torch_.float64, device="cuda"))
+        obs = env.reset().clone()
+        a = (torch_.rand(n, 2, dtype=torch_.float64, device="cuda") - 0.5) * 0.1
+        nxt = ag.forward_kinematics((obs[:, 0] + a[:, 0]).contiguous(), (obs[:, 1] + a[:, 1]).contiguous())[:, 2:4]
+        tg = nxt.clone(); tg[far] += 0.05
+        if graph:
+            env.capture()
+        env.set_targets(tg)
+        _, r, term, _, info = env.step(a)
+        assert torch_.equal(term & ~info["collision"], ~far & ~info["collision"]) and bool(term[~far].all())
