@@ -799,3 +799,24 @@ def test_per_env_targets(ag, torch_):
         env.set_targets(tg)
         _, r, term, _, info = env.step(a)
         assert torch_.equal(term & ~info["collision"], ~far & ~info["collision"]) and bool(term[~far].all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk_steps,chunk_envs", [(0, 512), (3, 1 << 17)])
+def test_rollout_host_heterogeneous_grids(ag, torch_, chunk_steps, chunk_envs):
+    """host-buffer pipeline on per-batch 64x64 maps (the lane-asynchronous kernel, staged grids): both slicing modes
+    equal one device rollout"""
+    n, K = 2048, 10
+    rng = np.random.default_rng(91)
+    occs = np.stack([random_grid(rng, 64, 0.01) for _ in range(8)])
+    g = ag.BatchedOccupancyGrid(torch_.as_tensor(occs, device="cuda"), 256)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    acts = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32)
+    a, b = make_scene(ag, torch_, g, j1, j2, seed=5), make_scene(ag, torch_, g, j1, j2, seed=5)
+    ra = a.rollout(K, actions=torch_.as_tensor(acts, device="cuda"))
+    out = b.alloc_records(K, pinned_host=True)
+    b.rollout_host(K, torch_.as_tensor(acts).pin_memory(), out, chunk_envs=chunk_envs, chunk_steps=chunk_steps)
+    for k in ("j1", "j2", "reward", "flags"):
+        assert np.array_equal(ra[k].cpu().numpy(), out[k].numpy()), k
+    assert a.stats_dict() == b.stats_dict() and a.stats_dict()["episodes"] > 100
+    assert torch_.equal(a.robot.joint_1, b.robot.joint_1) and torch_.equal(a.reset_ctr, b.reset_ctr)
