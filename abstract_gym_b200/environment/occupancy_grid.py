@@ -205,5 +205,27 @@ class BatchedOccupancyGrid:
         occ = torch.rand(n_grids, size, size, device=dev, generator=generator) < obstacle_probability
         return cls(occ, envs_per_grid, environment_size, dev)
 
+    @classmethod
+    def clustered(cls, n_grids, size, n_blobs, blob_radius_cells, envs_per_grid, clear_radius=0.12, environment_size=1.6,
+                  device=None, generator=None):
+        """Clustered obstacles for high-resolution maps (i.i.d. dense cells leave no free pose at
+        1024x1024): `n_blobs` discs of `blob_radius_cells` cells per grid at uniform random centres, with a disc of
+        `clear_radius` metres around the arm's base kept free so that free poses exist.  Set-up code (torch on the
+        device), not part of the step path."""
+        dev = require_cuda(device)
+        S = int(size)
+        side = environment_size / (S - 1)
+        idx = torch.arange(S, device=dev, dtype=torch.float32)
+        cx = (torch.rand(n_grids, n_blobs, device=dev, generator=generator) * S).view(n_grids, n_blobs, 1, 1)
+        cy = (torch.rand(n_grids, n_blobs, device=dev, generator=generator) * S).view(n_grids, n_blobs, 1, 1)
+        rr = (idx.view(1, 1, S, 1) - cy) ** 2 + (idx.view(1, 1, 1, S) - cx) ** 2        # [G, B, row, col]
+        occ = (rr <= float(blob_radius_cells) ** 2).any(dim=1)
+        # cell centres in metres (occupancy_grid.py:59-67: col c -> x = c*side - E/2, row r -> y = E/2 - r*side, + side/2)
+        xc = idx * side - environment_size / 2 + side / 2
+        yc = environment_size / 2 - idx * side + side / 2
+        clear = (yc.view(S, 1) ** 2 + xc.view(1, S) ** 2) <= (clear_radius + side) ** 2
+        occ &= ~clear.view(1, S, S)
+        return cls(occ, envs_per_grid, environment_size, dev)
+
     def device_grid(self, device=None) -> DeviceGrid:
         return self._grid

@@ -820,3 +820,23 @@ def test_rollout_host_heterogeneous_grids(ag, torch_, chunk_steps, chunk_envs):
         assert np.array_equal(ra[k].cpu().numpy(), out[k].numpy()), k
     assert a.stats_dict() == b.stats_dict() and a.stats_dict()["episodes"] > 100
     assert torch_.equal(a.robot.joint_1, b.robot.joint_1) and torch_.equal(a.reset_ctr, b.reset_ctr)
+
+
+@pytest.mark.gpu
+def test_clustered_grid_generator(ag, torch_, oracle):
+    """clustered-obstacle maps: a usable fraction of poses stays free, and rollouts on them equal the oracle"""
+    gen = torch_.Generator(device="cuda").manual_seed(7)
+    bg = ag.BatchedOccupancyGrid.clustered(4, 128, n_blobs=10, blob_radius_cells=4, envs_per_grid=256, generator=gen)
+    occ = bg.device_grid().unpack()
+    assert occ.shape == (4, 128, 128) and 0.005 < occ.mean() < 0.2
+    n, K = 1024, 12
+    rng = np.random.default_rng(92)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    sc = make_scene(ag, torch_, bg, j1, j2, seed=9)
+    free = 1.0 - float(sc.collision_check().float().mean().item())
+    assert free > 0.15, free
+    acts = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32)
+    st = oracle.RolloutState(j1, j2)
+    rec, stats = oracle.rollout(st, K, [oracle.grid_squares(o)[0] for o in occ], envs_per_grid=256, seed=9, actions_f32=acts)
+    drec = sc.rollout(K, actions=torch_.as_tensor(acts, device="cuda"))
+    assert np.array_equal(drec["flags"].cpu().numpy(), rec["flags"]) and np.array_equal(sc.stats.cpu().numpy(), stats)
