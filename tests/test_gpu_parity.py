@@ -840,3 +840,23 @@ def test_clustered_grid_generator(ag, torch_, oracle):
     rec, stats = oracle.rollout(st, K, [oracle.grid_squares(o)[0] for o in occ], envs_per_grid=256, seed=9, actions_f32=acts)
     drec = sc.rollout(K, actions=torch_.as_tensor(acts, device="cuda"))
     assert np.array_equal(drec["flags"].cpu().numpy(), rec["flags"]) and np.array_equal(sc.stats.cpu().numpy(), stats)
+
+
+@pytest.mark.gpu
+def test_rollout_random_grids_sweep(ag, torch_, oracle):
+    """24 random maps of every class (obstacle-list, traversal, staged with transposed bits, per-batch) x scripted /
+    Philox draws: FAST rollouts equal the oracle record for record"""
+    rng = np.random.default_rng(2027)
+    cases = 0
+    for i in range(24):
+        S = int(rng.choice([5, 7, 9, 12, 17, 31, 33, 48, 64, 100, 128]))
+        p = float(rng.choice([0.01, 0.03, 0.08])) if S <= 31 else float(rng.choice([0.004, 0.01]))
+        n = int(rng.choice([96, 256, 1000, 2048]))
+        K = int(rng.integers(2, 20))
+        if i % 3 == 2 and S > 9:
+            occs = [random_grid(rng, S, p) for _ in range(max(1, n // 256))]
+            _rollout_case(ag, torch_, oracle, occs, (n // 256) * 256 or 256, K, "fast", bool(i % 2), envs_per_grid=256, seed=100 + i)
+        else:
+            _rollout_case(ag, torch_, oracle, [random_grid(rng, S, p)], n, K, "fast", bool(i % 2), seed=100 + i)
+        cases += 1
+    assert cases == 24
