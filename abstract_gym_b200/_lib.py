@@ -11,7 +11,7 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 ENGINE_EXACT, ENGINE_FAST, ENGINE_BRUTE = 0, 1, 2
 ENGINES = {"exact": ENGINE_EXACT, "fast": ENGINE_FAST, "brute": ENGINE_BRUTE}
 FLAG_COLLISION, FLAG_DONE = 1, 2
@@ -55,7 +55,7 @@ class RolloutArgs(C.Structure):
                 ("j1", C.c_void_p), ("j2", C.c_void_p), ("reward", C.c_void_p), ("flags", C.c_void_p),
                 ("step_ctr", C.c_void_p), ("reset_ctr", C.c_void_p), ("ep_len", C.c_void_p),
                 ("rec_j1", C.c_void_p), ("rec_j2", C.c_void_p), ("rec_reward", C.c_void_p),
-                ("rec_flags", C.c_void_p), ("stats", C.c_void_p), ("diag", C.c_void_p)]
+                ("rec_flags", C.c_void_p), ("stats", C.c_void_p), ("diag", C.c_void_p), ("targets", C.c_void_p)]
 
 
 # every symbol include/abstract_gym_b200.h declares: (restype, argtypes)

@@ -246,6 +246,13 @@ __device__ __forceinline__ bool target_reached_cart(const ag_params &P, const Ar
 __device__ __forceinline__ bool target_reached(const ag_params &P, double j1, double j2, const Arm &A) {
     return P.choose_j_tar ? target_reached_joint(P, j1, j2) : target_reached_cart(P, A);
 }
+// tgt: per-env override of Scene.target_c (double[2]) or nullptr
+__device__ __forceinline__ bool target_reached_at(const ag_params &P, double j1, double j2, const Arm &A, const double *tgt) {
+    if (P.choose_j_tar) return target_reached_joint(P, j1, j2);
+    if (tgt == nullptr) return target_reached_cart(P, A);
+    const double2 t = *reinterpret_cast<const double2 *>(tgt);
+    return fabs(__dsub_rn(t.x, A.gx)) < P.reach_eps && fabs(__dsub_rn(t.y, A.gy)) < P.reach_eps;   // :129-130
+}
 
 // ---------------------------------------------------------------- shared-memory staging of the grid
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

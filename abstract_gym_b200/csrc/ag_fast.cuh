@@ -25,9 +25,9 @@
 
 // cold paths: out of line (ABI call) or inlined; see DESIGN.md "register allocation of K4"
 #ifdef AG_COLD_INLINE
-#define AG_COLD __device__ __forceinline__
+#define AG_COLD static __device__ __forceinline__
 #else
-#define AG_COLD __device__ __noinline__
+#define AG_COLD static __device__ __noinline__
 #endif
 
 namespace agd {
@@ -239,7 +239,9 @@ __device__ __forceinline__ float broad_list(const FastList &fl, const ArmF &a) {
 
 // 0 / 1 certain, 2 undecided.  Warp-uniform loop over the (few) obstacles: the broad-phase measures pick
 // the (link, square) pairs, then the narrow phase runs on the surviving pairs.
-__device__ __forceinline__ int arm_fast_list(const FastList *fl, const ArmF &a, const FastConst &C) {
+// Broad phase over the obstacle list: bit 2k = link 1 may touch square k, bit 2k+1 = link 2 may touch square k.
+// check_link1 = false: the caller already knows that link 1 is clear of every square (the hazard bit of ag_rollout_lut.cu)
+__device__ __forceinline__ uint32_t list_candidates(const FastList *fl, const ArmF &a, bool check_link1 = true) {
     const int m = fl->m;
     const float hm = fl->hm;
     const ArmBoxes bx = make_arm_boxes(a);
@@ -248,10 +250,14 @@ __device__ __forceinline__ int arm_fast_list(const FastList *fl, const ArmF &a, 
     for (int k = 0; k < m; ++k) {
         float m1, m2;
         box_measures(bx, fl->ctr[k], m1, m2);
-        cand |= ((m1 < hm ? 1u : 0u) | (m2 < hm ? 2u : 0u)) << (2 * k);
+        cand |= (((check_link1 && m1 < hm) ? 1u : 0u) | (m2 < hm ? 2u : 0u)) << (2 * k);
     }
-    // narrow phase on the surviving (link, cell) pairs; the link is rebuilt per pair from `a`
-    // (a dozen instructions) instead of keeping two LinkF live: registers matter more here
+    return cand;
+}
+
+// Narrow phase on the surviving (link, cell) pairs: 0 / 1 certain, 2 undecided.  The link is rebuilt per pair from `a`
+// (a dozen instructions) instead of keeping two LinkF live: registers matter more here.
+__device__ __forceinline__ int narrow_candidates(const FastList *fl, const ArmF &a, const FastConst &C, uint32_t cand) {
     int result = 0;
 #pragma unroll 1
     while (cand) {
@@ -266,6 +272,12 @@ __device__ __forceinline__ int arm_fast_list(const FastList *fl, const ArmF &a, 
         result |= v;
     }
     return result;
+}
+
+// 0 / 1 certain, 2 undecided.  Warp-uniform loop over the (few) obstacles: the broad-phase measures pick
+// the (link, square) pairs, then the narrow phase runs on the surviving pairs.
+__device__ __forceinline__ int arm_fast_list(const FastList *fl, const ArmF &a, const FastConst &C, bool check_link1 = true) {
+    return narrow_candidates(fl, a, C, list_candidates(fl, a, check_link1));
 }
 
 // ---------------------------------------------------------------- traversal broad phase (any grid), one link
@@ -395,13 +407,14 @@ __device__ __forceinline__ int arm_fast(const GridDev &G, const GridView &V, con
 }
 
 // reach test filter, scenario/scene_0.py:129-130 ; 0/1 certain, 2 undecided
-__device__ __forceinline__ int reach_fast(const FastConst &C, const ArmF &a) {
+__device__ __forceinline__ int reach_fast_at(const FastConst &C, const ArmF &a, float tx, float ty) {
     const float m = AG_DELTA_P + 2.0e-7f;
-    const float worst = fmaxf(fabsf(C.tx - a.gx), fabsf(C.ty - a.gy));    // reached <=> worst < eps
+    const float worst = fmaxf(fabsf(tx - a.gx), fabsf(ty - a.gy));        // reached <=> worst < eps
     if (worst > C.reach_eps + m) return 0;
     if (worst < C.reach_eps - m) return 1;
     return 2;
 }
+__device__ __forceinline__ int reach_fast(const FastConst &C, const ArmF &a) { return reach_fast_at(C, a, C.tx, C.ty); }
 
 // ---------------------------------------------------------------- cold path: the float64 reference arithmetic
 // Kept out of line so that the hot loop's register allocation is not dictated by it.
@@ -454,30 +467,42 @@ __device__ __forceinline__ int arm_f64_list(const GridDev &G, const FastList *fl
 // ---------------------------------------------------------------- cold path: float64
 // Kept out of line so that the hot loop's register allocation is not dictated by it.
 // c / r: the float32 filter's verdicts (0, 1, or 2 = undecided).
-AG_COLD int cold_exact_decide(const ag_params &P, const GridDev &G, const GridView &V, const FastList *fl, double q1,
-                              double q2, int c, int r) {
+// (tx, ty): the cartesian target of this env (Scene.target_c, or its per-env override)
+AG_COLD int cold_exact_decide_at(const ag_params &P, const GridDev &G, const GridView &V, const FastList *fl, double q1,
+                                 double q2, int c, int r, double tx, double ty) {
     const Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
     int fh = 0, axis = 0;
     if (c == 2 && fl != nullptr && fl->m >= 0) c = arm_f64_list(G, fl, A);
     const bool hit = (c == 2) ? arm_collides<AG_ENGINE_EXACT, false>(G, V, A, P.section_eps, fh, axis) : (c == 1);
-    const bool reached = (r == 2) ? target_reached_cart(P, A) : (r == 1);
+    const bool reached = (r == 2) ? (fabs(__dsub_rn(tx, A.gx)) < P.reach_eps && fabs(__dsub_rn(ty, A.gy)) < P.reach_eps)   // scene_0.py:129-130
+                                  : (r == 1);
     return (hit ? 1 : 0) | (reached ? 2 : 0) | (axis << 2);
+}
+__device__ __forceinline__ int cold_exact_decide(const ag_params &P, const GridDev &G, const GridView &V, const FastList *fl,
+                                                 double q1, double q2, int c, int r) {
+    return cold_exact_decide_at(P, G, V, fl, q1, q2, c, r, P.target_x, P.target_y);
 }
 
 // One step's two decisions for the FAST engine: bit0 collision, bit1 target reached, bits 2.. axis-aligned count.
 // want_reach=false (reset candidates, K2, K3): only the collision bit is meaningful.
+// tgt: this env's cartesian target (double[2], per-env override of Scene.target_c) or nullptr = P.target_x/y
 template <int BP>
 __device__ __forceinline__ int fast_decide(const ag_params &P, const GridDev &G, const GridView &V, const FastList *fl,
-                                           const FastConst &C, double q1, double q2, bool want_reach) {
+                                           const FastConst &C, double q1, double q2, bool want_reach,
+                                           const double *tgt = nullptr) {
     bool ok;
     const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
     const int c = ok ? arm_fast<BP>(G, V, fl, C, a) : 2;
     int r = 0;
+    double txd = P.target_x, tyd = P.target_y;
     if (want_reach) {
         if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
-        else r = ok ? reach_fast(C, a) : 2;
+        else {
+            if (tgt != nullptr) { const double2 t2 = *reinterpret_cast<const double2 *>(tgt); txd = t2.x; tyd = t2.y; }
+            r = ok ? reach_fast_at(C, a, (float)txd, (float)tyd) : 2;
+        }
     }
-    if (c == 2 || r == 2) return cold_exact_decide(P, G, V, fl, q1, q2, c, r);
+    if (c == 2 || r == 2) return cold_exact_decide_at(P, G, V, fl, q1, q2, c, r, txd, tyd);
     return c | (r << 1);
 }
 

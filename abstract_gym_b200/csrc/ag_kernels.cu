@@ -5,81 +5,20 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "ag_device.cuh"
-#include "ag_fast.cuh"
+#include "ag_rollout.cuh"
 
 using namespace agd;
 
+// ag_rollout_lut.cu: the persistent kernel for scene_0-class grids (obstacle list, one grid, cartesian target)
+bool rollout_lut_applies(const ag_params &P, const GridDev &G, const RolloutDev &A);
+ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s);
+
 namespace {
 
-constexpr int AG_BLOCK = 256;
 #ifndef AG_FAST_BLOCKS_PER_SM
 #define AG_FAST_BLOCKS_PER_SM 4
 #endif
 std::atomic<long long> g_launches{0};
-
-struct RolloutDev {
-    int64_t n, env_id0, row_stride;
-    int32_t K, R;
-    uint64_t seed;
-    const float *actions;
-    const double *reset_u;
-    double *j1, *j2;
-    float *reward;
-    uint8_t *flags;
-    uint32_t *step_ctr, *reset_ctr, *ep_len;
-    float *rec_j1, *rec_j2, *rec_reward;
-    uint8_t *rec_flags;
-    unsigned long long *stats;
-    unsigned long long *diag;
-    int32_t zfill;            // 1: the reward / flags planes of this launch are zero-filled up front by each warp
-};
-
-// ------------------------------------------------------------------------- per-block context
-// Every kernel that reads the grid starts the same way: stage the block's grid into shared memory
-// (or point at global memory), and for the FAST engine build the obstacle list of small sparse grids.
-struct BlockCtx {
-    GridView V;
-    const FastList *fl;   // nullptr: not applicable (grid not staged / engine != FAST)
-};
-
-template <int ENGINE>
-__device__ __forceinline__ BlockCtx block_prologue(const GridDev &G, int64_t env_id0, int64_t n, unsigned char *smem,
-                                                   FastList *s_fl) {
-    const int64_t e0 = (int64_t)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
-    BlockCtx B;
-    B.fl = nullptr;
-    if (G.stage) {
-        B.V = stage_grid(G, env_id0 + e0, smem);
-        if (ENGINE == AG_ENGINE_FAST) {
-            build_fast_list(G, B.V, s_fl);
-            B.fl = s_fl;
-        }
-    } else {
-        const int64_t off = grid_of_env(G, env_id0 + min(e, n - 1)) * G.stride_words;
-        B.V.bits = G.bits + off;
-        B.V.bits_t = G.bits_t ? G.bits_t + off : nullptr;
-        B.V.min_x = G.min_x; B.V.min_y = G.min_y;
-    }
-    return B;
-}
-
-// Block statistics: shared-memory atomics at (rare) events, one global atomic per slot per block.
-// 64-bit shared atomics compile to compare-and-swap spin loops (ATOMS.CAST.SPIN), so every slot but the
-// episode-length sum is accumulated as a native 32-bit add on the low word of its 64-bit cell: a block adds at
-// most blockDim * K (K <= AG_MAX_K) per slot and launch, which cannot carry.  The return slot is signed.
-constexpr int AG_MAX_K = 65536;
-__device__ __forceinline__ void acc32(unsigned long long *s_acc, int slot, int v) {
-    atomicAdd(reinterpret_cast<unsigned int *>(&s_acc[slot]), (unsigned int)v);
-}
-__device__ __forceinline__ void stats_flush(unsigned long long *s_acc, unsigned long long *gstats) {
-    __syncthreads();
-    if (threadIdx.x < AG_ST_COUNT && gstats != nullptr) {
-        unsigned long long v = s_acc[threadIdx.x];
-        if (threadIdx.x == AG_ST_RETURN_MILLI) v = (unsigned long long)(long long)(int)(unsigned int)v;   // sign-extend
-        if (v != 0) atomicAdd(&gstats[threadIdx.x], v);
-    }
-}
 
 // ------------------------------------------------------------------------------------------- K5
 // environment/occupancy_grid.py:35-37,85-90: matrix -> set of occupied cells, here one bit per cell.
@@ -169,21 +108,6 @@ __global__ void k_move_to_joint_pose(double *__restrict__ j1, double *__restrict
     j1[i] = a; j2[i] = b;
 }
 
-// collision_check of one pose for K2/K3 (flag only unless WANT_FIRST)
-template <int ENGINE, bool WANT_FIRST, int BP = BP_ANY>
-__device__ __forceinline__ bool pose_collides(const ag_params &P, const GridDev &G, const BlockCtx &B,
-                                              const FastConst &C, double j1, double j2, int &fh, int &axis) {
-    if constexpr (ENGINE == AG_ENGINE_FAST && !WANT_FIRST) {
-        const int d = fast_decide<BP>(P, G, B.V, B.fl, C, j1, j2, false);
-        axis += d >> 2;
-        return d & 1;
-    } else {
-        const Arm A = forward_kinematics(j1, j2, P.link_1, P.link_2);
-        return arm_collides<ENGINE == AG_ENGINE_BRUTE ? AG_ENGINE_BRUTE : AG_ENGINE_EXACT, WANT_FIRST>(
-            G, B.V, A, P.section_eps, fh, axis);
-    }
-}
-
 // ------------------------------------------------------------------------------------------- K2
 template <int ENGINE, bool WANT_FIRST>
 __global__ void __launch_bounds__(AG_BLOCK) k_collision(const ag_params P, const GridDev G,
@@ -259,35 +183,6 @@ __global__ void __launch_bounds__(AG_BLOCK) k_step(const ag_params P, const Grid
     stats_flush(s_acc, stats);
 }
 
-// shared by K3 and K4: scenario/scene_0.py:174-181 with a bound.  `colliding` is the
-// collision_check() of the current pose.
-template <int ENGINE, bool HAS_RESET_U, int BP = BP_ANY>
-__device__ __forceinline__ void resample_pose(const ag_params &P, const GridDev &G, const BlockCtx &B,
-                                              const FastConst &C, bool colliding, double &j1, double &j2,
-                                              uint32_t &rc, const double *reset_u_env, int32_t R, uint64_t seed,
-                                              uint64_t gid, unsigned long long *s_acc) {
-    int tries = 0;
-    while (colliding) {
-        if (tries >= P.max_reset_tries || (HAS_RESET_U && rc >= (uint32_t)R)) {
-            acc32(s_acc, AG_ST_STUCK_RESETS, 1);
-            break;
-        }
-        double u0, u1;
-        if (HAS_RESET_U) {
-            const double2 u = reinterpret_cast<const double2 *>(reset_u_env)[rc];
-            u0 = u.x; u1 = u.y;
-        } else {
-            philox_uniform2(seed, gid, rc, 1u, u0, u1);
-        }
-        ++rc; ++tries;
-        j1 = __dmul_rn(__dmul_rn(u0, 3.141592653589793), 2.0);    // scene_0.py:180  rand()*pi*2.0
-        j2 = __dmul_rn(__dmul_rn(u1, 3.141592653589793), 2.0);    // :181
-        int fh = 0, axis = 0;
-        colliding = pose_collides<ENGINE, false, BP>(P, G, B, C, j1, j2, fh, axis);
-        if (axis) acc32(s_acc, AG_ST_AXIS_ALIGNED, axis);
-    }
-}
-
 // ------------------------------------------------------------------------------------------- K3
 // scenario/scene_0.py:105-113 (clear_flags) / :174-181
 template <int ENGINE, bool HAS_RESET_U>
@@ -328,14 +223,14 @@ __global__ void __launch_bounds__(AG_BLOCK) k_reset(const ag_params P, const Gri
 // inside the out-of-line cold_terminal(), so the loop fits the register budget without spills.
 template <int ENGINE, int BP>
 __device__ __forceinline__ int step_decide(const ag_params &P, const GridDev &G, const BlockCtx &B,
-                                           const FastConst &C, double q1, double q2) {
+                                           const FastConst &C, double q1, double q2, const double *tgt) {
     if constexpr (ENGINE == AG_ENGINE_FAST) {
-        return fast_decide<BP>(P, G, B.V, B.fl, C, q1, q2, true);
+        return fast_decide<BP>(P, G, B.V, B.fl, C, q1, q2, true, tgt);
     } else {
         const Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
         int fh = 0, axis = 0;
         const bool h = arm_collides<ENGINE, false>(G, B.V, A, P.section_eps, fh, axis);
-        return (h ? 1 : 0) | (target_reached(P, q1, q2, A) ? 2 : 0) | (axis << 2);
+        return (h ? 1 : 0) | (target_reached_at(P, q1, q2, A, tgt) ? 2 : 0) | (axis << 2);
     }
 }
 
@@ -356,76 +251,11 @@ struct HotShared {
     int undecided[BLOCK];       // 0, or 16 | c | r << 2: the float32 filter's verdicts (2 = undecided) of step t
 };
 
-// this thread's view of its grid: the block's shared-memory copy (layout of stage_grid) or global memory
-__device__ __forceinline__ GridView thread_view(const GridDev &G, unsigned char *smem, int64_t gid) {
-    GridView V;
-    if (G.stage) {
-        const int spad = (G.S + 1) & ~1;
-        const uint32_t bit_bytes = (uint32_t)G.stride_words * 4u;
-        V.bits = reinterpret_cast<const uint32_t *>(smem + 16);
-        V.bits_t = G.bits_t ? V.bits + G.stride_words : nullptr;
-        V.min_x = reinterpret_cast<const double *>(smem + 16 + (G.bits_t ? 2u * bit_bytes : bit_bytes));
-        V.min_y = V.min_x + spad;
-    } else {
-        const int64_t off = grid_of_env(G, gid) * G.stride_words;
-        V.bits = G.bits + off;
-        V.bits_t = G.bits_t ? G.bits_t + off : nullptr;
-        V.min_x = G.min_x; V.min_y = G.min_y;
-    }
-    return V;
-}
-
 // Action prefetch ring: every thread streams its own actions global -> shared with cp.async (LDGSTS), AG_RING - 1
 // steps ahead of their use, so that no register and no warp ever waits for a DRAM round trip (with a
 // register prefetch one step ahead, 37 % of all stall samples were long-scoreboard waits on that load:
 // profiles/r1g).  Slot (t mod AG_RING) of row threadIdx.x holds the action of step t.
 constexpr int AG_RING = 4;
-
-__device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// one step record (experiment_0.py:23-25): joint_1, joint_2, step_reward, flags, post-step / pre-reset
-template <bool RECORD>
-__device__ __forceinline__ void store_record(const RolloutDev &A, int64_t o, double q1, double q2, float rw, uint32_t fl) {
-    if (RECORD) {
-        __stcs(A.rec_j1 + o, (float)q1);
-        __stcs(A.rec_j2 + o, (float)q2);
-        __stcs(A.rec_reward + o, rw);
-        A.rec_flags[o] = (uint8_t)fl;
-    }
-}
-
-// The record of an UNEVENTFUL step has reward 0 and flags 0.  When the launch qualifies (complete warps, 16-byte
-// aligned rows) every warp zero-fills its slice of those two planes once, with warp-wide 16-byte stores (20 stores
-// for 64 steps), and the hot loop stores the two joints only; eventful steps rewrite all four fields.
-template <bool RECORD>
-__device__ __forceinline__ void store_uneventful(const RolloutDev &A, int64_t o, double q1, double q2) {
-    if (RECORD) {
-        __stcs(A.rec_j1 + o, (float)q1);
-        __stcs(A.rec_j2 + o, (float)q2);
-        if (!A.zfill) {
-            __stcs(A.rec_reward + o, 0.0f);
-            A.rec_flags[o] = 0;
-        }
-    }
-}
-
-// warp-cooperative zero fill of rows [0, K) x this warp's 32 envs of the reward (128 B per row) and flags (32 B per
-// row) planes.  warp_e0: first env of the warp (a multiple of 32).
-__device__ __forceinline__ void zero_fill_warp(const RolloutDev &A, int64_t warp_e0) {
-    const int lane = threadIdx.x & 31;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = lane >> 3; t < A.K; t += 4)            // 8 lanes x 16 B = one 128-byte row segment; 4 rows per store
-        __stcs(reinterpret_cast<float4 *>(A.rec_reward + (int64_t)t * A.row_stride + warp_e0) + (lane & 7), z4);
-    const uint4 zu = make_uint4(0u, 0u, 0u, 0u);
-    for (int t = lane >> 1; t < A.K; t += 16)           // 2 lanes x 16 B = one 32-byte row segment; 16 rows per store
-        reinterpret_cast<uint4 *>(A.rec_flags + (int64_t)t * A.row_stride + warp_e0)[lane & 1] = zu;
-    __syncwarp();                                       // orders these stores before the owners' later rewrites
-}
 
 // Cold section, out of line: (1) finish a step whose float32 filter was undecided with the
 // float64 reference arithmetic, (2) episode end (experiment_0.py:30-34): statistics + Scene.reset().
@@ -445,7 +275,9 @@ __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, 
     B.fl = fl_list;
     if (und) {
         acc32(s_acc, AG_ST_COUNT + AG_DIAG_EXACT_STEPS, 1);
-        d = cold_exact_decide(P, G, B.V, B.fl, q1, q2, und & 3, (und >> 2) & 3);  // the filter's verdicts
+        double txd = P.target_x, tyd = P.target_y;
+        if (A.targets != nullptr) { const double2 tg = reinterpret_cast<const double2 *>(A.targets)[e]; txd = tg.x; tyd = tg.y; }
+        d = cold_exact_decide_at(P, G, B.V, B.fl, q1, q2, und & 3, (und >> 2) & 3, txd, tyd);  // the filter's verdicts
         if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
         if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
         store_record<RECORD>(A, hs.o[x], q1, q2, rw, fl);                         // experiment_0.py:23-25
@@ -521,6 +353,9 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
         const uint32_t sc0 = A.step_ctr[e0];
         A.step_ctr[e0] = sc0 + (uint32_t)A.K;
         const float reach_thr_clean = C.reach_eps + (AG_DELTA_P + 2.0e-7f);      // reach_fast()'s margin
+        const double *tgt = A.targets ? A.targets + 2 * e0 : nullptr;            // per-env target override
+        float ltx = C.tx, lty = C.ty;
+        if (tgt != nullptr) { ltx = (float)tgt[0]; lty = (float)tgt[1]; }
         for (;;) {                                                               // ---- outer
             // hot state: struct -> registers
             double q1 = hs.q1[x], q2 = hs.q2[x];
@@ -561,7 +396,7 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                         bool ok;
                         const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
                         const float sep = broad_list(s_fl, a);
-                        const float worst = fmaxf(fabsf(C.tx - a.gx), fabsf(C.ty - a.gy));
+                        const float worst = fmaxf(fabsf(ltx - a.gx), fabsf(lty - a.gy));
                         slow = !(sep >= s_fl.hm) | !(worst >= reach_thr) | !ok;             // NaN-safe: NaN is slow
                         if (P.choose_j_tar) slow |= target_reached_joint(P, q1, q2);
                         if (slow) s_arm[threadIdx.x] = make_float4(a.ex, a.ey, ok ? a.gx : __int_as_float(0x7fc00000), a.gy);
@@ -604,12 +439,12 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                         const int c = (ok && s_fl.m >= 0) ? (FULL ? c_coop : arm_fast_list(&s_fl, a, C)) : 2;
                         int r;
                         if (P.choose_j_tar) r = target_reached_joint(P, q1, q2) ? 1 : 0;
-                        else r = ok ? reach_fast(C, a) : 2;
+                        else r = ok ? reach_fast_at(C, a, ltx, lty) : 2;
                         undecided = ((c | r) & 2) != 0;
                         cr = c | (r << 2);
                         d = (c & 1) | ((r & 1) << 1);
                     } else {
-                        d = step_decide<ENGINE, BP>(P, G, B, C, q1, q2);
+                        d = step_decide<ENGINE, BP>(P, G, B, C, q1, q2, tgt);
                     }
                     event = undecided;
                     if (!undecided) {
@@ -680,6 +515,7 @@ k_rollout_async(const __grid_constant__ ag_params P, const __grid_constant__ Gri
         A.step_ctr[e] = sc0 + (uint32_t)A.K;
         const uint64_t gid = (uint64_t)(A.env_id0 + e);
         const double *ru = HAS_RESET_U ? A.reset_u + e * A.R * 2 : nullptr;
+        const double *tgt = A.targets ? A.targets + 2 * e : nullptr;             // per-env target override
         int t = 0, tries = 0;
         bool resetting = false;
         while (t < A.K || resetting) {
@@ -713,7 +549,7 @@ k_rollout_async(const __grid_constant__ ag_params P, const __grid_constant__ Gri
             }
             // ---- one pose check per lane and iteration, whatever the mode, with all lanes converged
             __syncwarp(live);
-            const int d = stuck ? 0 : fast_decide<BP>(P, G, B.V, B.fl, C, q1, q2, !resetting);
+            const int d = stuck ? 0 : fast_decide<BP>(P, G, B.V, B.fl, C, q1, q2, !resetting, tgt);
             __syncwarp(live);
             loc[AG_ST_AXIS_ALIGNED] += d >> 2;
             if (!resetting) {
@@ -780,10 +616,16 @@ ag_status make_grid_dev(const ag_params *p, const ag_grid *g, int64_t env_id0, i
     return AG_OK;
 }
 
+// Without the opt-in a launch may use 48 KB of shared memory INCLUDING the kernel's static part (the 256-thread
+// rollout kernels carry ~22 KB of it), so the attribute is set whenever static + dynamic exceeds 48 KB.
 template <typename Kern>
 ag_status set_smem(Kern k, size_t smem) {
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem == 0) return AG_OK;
+    cudaFuncAttributes at;
+    cudaError_t e = cudaFuncGetAttributes(&at, k);
+    if (e != cudaSuccess) return (ag_status)e;
+    if (smem + at.sharedSizeBytes > 48 * 1024 && (int)smem > at.maxDynamicSharedSizeBytes) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (ag_status)e;
     }
     return AG_OK;
@@ -855,6 +697,8 @@ ag_status launch_rollout_e(const ag_params &P, const GridDev &G, const RolloutDe
 
 }  // namespace
 
+void ag_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 // internal (also used by ag_host.cu): rollout with explicit action/record row stride
 ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, int64_t row_stride,
                           void *stream) {
@@ -866,7 +710,7 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
     const int nrec = (a->rec_j1 != nullptr) + (a->rec_j2 != nullptr) + (a->rec_reward != nullptr) + (a->rec_flags != nullptr);
     if (nrec != 0 && nrec != 4) return AG_ERR_NULL;
     if (a->reset_u && a->R < 1) return AG_ERR_SHAPE;
-    if (((uintptr_t)a->actions % 8) || ((uintptr_t)a->reset_u % 16)) return AG_ERR_ALIGN;
+    if (((uintptr_t)a->actions % 8) || ((uintptr_t)a->reset_u % 16) || ((uintptr_t)a->targets % 16)) return AG_ERR_ALIGN;
     if (row_stride < a->n) return AG_ERR_SHAPE;
     GridDev G;
     size_t smem;
@@ -880,6 +724,7 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
     A.rec_j1 = a->rec_j1; A.rec_j2 = a->rec_j2; A.rec_reward = a->rec_reward; A.rec_flags = a->rec_flags;
     A.stats = reinterpret_cast<unsigned long long *>(a->stats);
     A.diag = reinterpret_cast<unsigned long long *>(a->diag);
+    A.targets = a->targets; A.max_occupied = g->max_occupied;
     // warp-wide 16-byte zero fill of the reward / flags record planes needs 16-byte aligned rows
     A.zfill = (a->rec_reward != nullptr && a->n % 32 == 0 && row_stride % 16 == 0 &&
                (uintptr_t)a->rec_reward % 16 == 0 && (uintptr_t)a->rec_flags % 16 == 0) ? 1 : 0;
@@ -888,6 +733,7 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
     // (ag_grid.max_occupied); a block whose grid turns out not to qualify falls back to EXACT per lane.
     if (a->engine == AG_ENGINE_FAST) {
         const bool list = G.stage && g->S <= 32 && g->max_occupied >= 0 && g->max_occupied <= AG_LIST_MAX;
+        if (list && rollout_lut_applies(*p, G, A)) return launch_rollout_lut(*p, G, A, smem, s);
         if (list) return launch_rollout_e<AG_ENGINE_FAST, BP_LIST>(*p, G, A, smem, s);
         return launch_rollout_e<AG_ENGINE_FAST, BP_TRAVERSAL>(*p, G, A, smem, s);
     }

@@ -1,0 +1,636 @@
+// ag_rollout_lut.cu -- K4 for scene_0-class grids (obstacle list, one grid, cartesian target): the rollout loop
+// experiment/experiment_0.py:20-34 fused over K steps, persistent warps, table-driven forward kinematics.
+//
+// Why a second form of K4 (DESIGN.md "K4, scene_0 class"): the general kernel (ag_kernels.cu, k_rollout) is
+// instruction-issue-bound at ~236 warp-instructions per warp-step; ~145 of them are the float32 filter of an
+// uneventful step (99.6 % of all env-steps), and of those ~60 are the float32 sine / cosine of the two joints and
+// link 1's box test.  Here the float32 arm comes from two shared-memory tables indexed by the joint phase:
+//
+//   x      = low word of fma(q, 2^32/2pi, 1.5*2^52)      one DFMA per joint: the turn fraction as a 32-bit integer
+//   entry  = lut[x >> (32-B)]                            (c, s) * length at the bin centre, 8 bytes
+//   d      = (x mod 2^(32-B)) * 2pi/2^32 - pi/2^B        angle from the bin centre, one LOP3 + one FFMA
+//   point  = (1 - d*d/2) * (c, s) + d * (-s, c)          second-order Taylor step: FMUL + FFMA + FMUL2 + 2 FFMA
+//
+// With 2048 bins for link 1 and 512 for link 2 the truncation error is below 2e-9 m / 2e-8 m; emulated op for op in
+// numpy over 1.2e7 angles up to +-2^20 rad the elbow is within 8.9e-8 m and link 2's half vector within 4.2e-8 m
+// of the float64 values, i.e. the end effector within 2.1e-7 m: inside the error budget AG_DELTA_P = 3e-7 m that
+// the float32 filter of ag_fast.cuh was derived for (its own polynomial arm measures 1.8e-7 m).  So the hot loop
+// runs the SAME decision as the general kernel's inner loop -- link-2 box test and reach pre-test with the same
+// thresholds -- on a cheaper arm.  Link 1 depends on joint_1 only: its test is folded into the table as one bit
+// per bin ("for some angle of this bin link 1 comes within 2e-6 m of a square"), computed exactly from the angular
+// interval each square subtends inside link 1's reach (hazard_interval).
+// A lane that clears all three tests is certainly uneventful; every other lane ("slow", ~0.5 % of env-steps) goes
+// through the float32 narrow phase, the float64 filter and the reference arithmetic exactly as in the general
+// kernel (slow_step).  Results are therefore identical to the general kernel's and the reference's;
+// tests/test_gpu_parity.py runs both.
+//
+// Structure: a persistent grid (one 256-thread block per SM slot); the block builds the tables once, every warp
+// then walks 32-env tiles (tile = warp index + i * #warps).  Per tile: state -> registers, the next valid reset
+// pose is drawn up front by all 32 lanes together (draw_valid_pose; consumed on collision, so an episode end costs
+// a few dozen instructions instead of a one-lane rejection loop), then K steps of
+//   action (register prefetch three rows ahead) -> 2 DADD -> table arm -> box test / reach pre-test ->
+//   record (2 F2F + 2 STG) -> vote.
+#include <atomic>
+#include <cstdlib>
+
+#include "ag_rollout.cuh"
+
+using namespace agd;
+
+void ag_note_launch();
+
+namespace {
+
+#ifndef AG_LUT_B1
+#define AG_LUT_B1 11
+#endif
+#ifndef AG_LUT_B2
+#define AG_LUT_B2 9
+#endif
+#ifndef AG_LUT_BLOCKS_PER_SM
+#define AG_LUT_BLOCKS_PER_SM 2
+#endif
+
+constexpr int B1 = AG_LUT_B1, B2 = AG_LUT_B2;            // bins: 2^B1 for link 1 (also the resolution of its hazard bit), 2^B2 for link 2
+constexpr int N1 = 1 << B1, N2 = 1 << B2;
+static_assert(B1 >= 9 && B2 >= 9 && B1 <= 11 && B2 <= 11, "sub-bin phase must fit 23 bits; tables must fit static shared memory");
+constexpr int LB = 256, LW = LB / 32;
+// Action prefetch ring: every lane streams its own actions global -> shared with cp.async (LDGSTS), RING - 1 steps
+// ahead of their use; slot (t mod RING) of the warp's ring holds row t.  (Register prefetch does not work here: ptxas
+// gives all in-flight LDGs of the loop ONE scoreboard slot, so a consumer waits for every outstanding load and the
+// effective distance is a single step: profiles/r2b.)
+constexpr int RING = 4;
+constexpr double PHASE_MAGIC = 6755399441055744.0;       // 1.5 * 2^52: the add rounds to an integer in the low word
+constexpr double TWO_PI = 6.283185307179586476925;
+constexpr float RAD_PER_UNIT = (float)(TWO_PI / 4294967296.0);   // one phase unit (2^-32 turn) in radians
+// d = fma(2^23 + frac, RAD_PER_UNIT, C0): removes the 2^23 of the integer -> float trick and half a bin
+__host__ __device__ constexpr float lut_c0(int bits) { return (float)(-(8388608.0 * (double)RAD_PER_UNIT + TWO_PI / (double)(2 << bits))); }
+constexpr float C0_1 = lut_c0(B1), C0_2 = lut_c0(B2);
+
+struct LutConst {
+    double phase_scale;     // 2^32 / 2pi
+    float thr_c;            // reach_eps + AG_DELTA_P + 2e-7: reach pre-test threshold (reach_fast's margin)
+    int64_t n_tiles;
+    uint32_t ss_off;        // byte offset of SlowShared in dynamic shared memory (after the staged grid)
+    uint32_t slot;          // this launch's pair of tile / done counters (g_tile_sched)
+};
+
+// Dynamic tile scheduling: warps draw 32-env tiles from a device-global counter, so no warp idles while tiles remain
+// (a static split leaves 13 % of all warp-time parked at the end: profiles/r2a).  Each launch uses the next of
+// AG_TILE_SLOTS counter pairs (host round-robin); the last block to finish zeroes its pair again.  Launches in flight
+// at the same time on one device must therefore number fewer than AG_TILE_SLOTS.
+constexpr int AG_TILE_SLOTS = 256;
+__device__ unsigned int g_tile_sched[2 * AG_TILE_SLOTS];    // [2*slot] next tile, [2*slot+1] blocks done
+
+// per-thread state that only the slow path touches (one slot per thread: no sharing, no conflicts)
+struct SlowShared {
+    double cq1[LB], cq2[LB];   // the pre-drawn reset pose
+    float rw[LB];              // sticky Scene.step_reward
+    uint32_t fl[LB];           // sticky flags
+    uint32_t rc[LB];           // reset draw counter
+    uint32_t crc[LB];          // reset draw counter after the pre-drawn pose
+    uint32_t cinfo[LB];        // PoseDraw::info of the pre-drawn pose, 0 = consumed
+    int el_off[LB];            // episode length after step t = el_off + t + 1
+    // the hot loop's registers, parked here around the slow section: that section makes out-of-line calls, and any
+    // value live in a register across a call is spilled where it is DEFINED, i.e. inside the hot loop
+    double q1[LB], q2[LB];
+    float thr[LB], tx[LB], ty[LB];
+    int t[LB];
+    int cr[LB];                // level 1's verdicts for level 2: 0 = no event, else 16 | c | r << 2
+    uint32_t sc0[LB];          // action draw counter at the start of the launch (Philox actions)
+};
+
+__device__ __forceinline__ void add64(unsigned long long *s_acc, int slot, long long v) {
+    atomicAdd(&s_acc[slot], (unsigned long long)v);
+}
+
+// scenario/scene_0.py:174-181 with a bound, entered with a colliding pose: draw candidates until one is free.
+// Nothing is counted here (the pose may never be used); the caller applies `info` when it consumes the pose.
+struct PoseDraw {
+    double j1, j2;
+    uint32_t rc;
+    uint32_t info;   // bit0 valid, bit1 at least one candidate drawn (j1, j2 meaningful), bit2 gave up; bits 8..: axis-aligned evaluations
+};
+enum { PD_VALID = 1, PD_DREW = 2, PD_STUCK = 4 };
+
+AG_COLD PoseDraw draw_valid_pose(const ag_params &P, const GridDev &G, const FastConst &C,
+                                                 const unsigned char *smem_grid, const FastList *fl, uint32_t rc,
+                                                 const double *reset_u_env, int32_t R, uint64_t seed, uint64_t gid) {
+    const GridView V = thread_view(G, const_cast<unsigned char *>(smem_grid), (int64_t)gid);
+    PoseDraw o;
+    o.j1 = 0.0; o.j2 = 0.0; o.info = PD_VALID;
+    int tries = 0, axis = 0;
+    bool colliding = true;
+    while (colliding) {
+        if (tries >= P.max_reset_tries || (reset_u_env != nullptr && rc >= (uint32_t)R)) { o.info |= PD_STUCK; break; }
+        double u0, u1;
+        if (reset_u_env != nullptr) {
+            const double2 u = reinterpret_cast<const double2 *>(reset_u_env)[rc];
+            u0 = u.x; u1 = u.y;
+        } else {
+            philox_uniform2(seed, gid, rc, 1u, u0, u1);
+        }
+        ++rc; ++tries;
+        o.j1 = __dmul_rn(__dmul_rn(u0, 3.141592653589793), 2.0);    // scene_0.py:180  rand()*pi*2.0
+        o.j2 = __dmul_rn(__dmul_rn(u1, 3.141592653589793), 2.0);    // :181
+        const int d = fast_decide<BP_LIST>(P, G, V, fl, C, o.j1, o.j2, false);
+        axis += d >> 2;
+        colliding = (d & 1) != 0;
+    }
+    if (tries) o.info |= PD_DREW;
+    o.info |= (uint32_t)axis << 8;
+    o.rc = rc;
+    return o;
+}
+
+// Level 2 of the slow path, for one lane with an event: (1) float64 filter / reference arithmetic for what the
+// float32 narrow phase could not settle, (2) reward / flags (scene_0.py:95-100), record rewrite, (3) episode end
+// (experiment_0.py:30-34): statistics + Scene.reset() from the pre-drawn pose.
+// Works on the lane's parked state (SlowShared: q1, q2, t, cr in; q1, q2, thr out).
+template <bool RECORD>
+__device__ __forceinline__ void settle_step(const ag_params &P, const GridDev &G, const FastConst &C, const RolloutDev &A,
+                                            SlowShared &ss, const FastList *fl, unsigned long long *s_acc,
+                                            const unsigned char *smem_grid, float thr_clean, int64_t e) {
+    const int x = threadIdx.x;
+    const int t = ss.t[x] - 1;                                                   // the step being settled (ss.t: where the loop resumes)
+    const int c = ss.cr[x] & 3, r = (ss.cr[x] >> 2) & 3;                         // the float32 verdicts: 0 / 1 certain, 2 undecided
+    double q1 = ss.q1[x], q2 = ss.q2[x];
+    int d = (c & 1) | ((r & 1) << 1);
+    bool cold = false;
+    if ((c | r) & 2) {                                                           // undecided: float64
+        double txd = P.target_x, tyd = P.target_y;
+        if (A.targets != nullptr) {
+            const double2 tg = reinterpret_cast<const double2 *>(A.targets)[e];
+            txd = tg.x; tyd = tg.y;
+        }
+        const GridView V = thread_view(G, const_cast<unsigned char *>(smem_grid), A.env_id0 + e);
+        d = cold_exact_decide_at(P, G, V, fl, q1, q2, c, r, txd, tyd);
+        cold = true;
+        if (A.diag != nullptr) add64(s_acc, AG_ST_COUNT + AG_DIAG_EXACT_STEPS, 1);
+    }
+    float rw = ss.rw[x];
+    uint32_t f = ss.fl[x];
+    if (d & 1) { rw = (float)P.reward_collision; f |= AG_FLAG_COLLISION; }       // scene_0.py:95-97
+    if (d & 2) { rw = (float)P.reward_reach; f |= AG_FLAG_DONE; }                // :98-100
+    if (d >> 2) add64(s_acc, AG_ST_AXIS_ALIGNED, d >> 2);
+    if (RECORD && (f != 0 || rw != 0.0f)) {                                      // experiment_0.py:23-25 (joints already stored)
+        const int64_t o = (int64_t)t * A.row_stride + e;
+        __stcs(A.rec_reward + o, rw);
+        A.rec_flags[o] = (uint8_t)f;
+    }
+    if (f) {                                                                     // experiment_0.py:30-34
+        cold = true;
+        add64(s_acc, AG_ST_EPISODES, 1);
+        if (f & AG_FLAG_COLLISION) add64(s_acc, AG_ST_COLLISIONS, 1);
+        if (f & AG_FLAG_DONE) add64(s_acc, AG_ST_SUCCESSES, 1);
+        add64(s_acc, AG_ST_EP_LEN_SUM, (long long)ss.el_off[x] + t + 1);
+        add64(s_acc, AG_ST_RETURN_MILLI, (long long)__float2int_rn(rw * 1e-3f));
+        if (d & 1) {   // Scene.reset(): the pose is unchanged since the step, so collision_check() == (d & 1)
+            uint32_t info = ss.cinfo[x];
+            if (info & PD_VALID) {
+                if (info & PD_DREW) { q1 = ss.cq1[x]; q2 = ss.cq2[x]; }
+                ss.rc[x] = ss.crc[x];
+                ss.cinfo[x] = 0;
+            } else {                                                             // second collision of this tile: draw now
+                const PoseDraw pd = draw_valid_pose(P, G, C, smem_grid, fl, ss.rc[x],
+                                                    A.reset_u ? A.reset_u + e * A.R * 2 : nullptr, A.R, A.seed,
+                                                    (uint64_t)(A.env_id0 + e));
+                if (pd.info & PD_DREW) { q1 = pd.j1; q2 = pd.j2; }
+                ss.rc[x] = pd.rc;
+                info = pd.info;
+            }
+            if (info & PD_STUCK) add64(s_acc, AG_ST_STUCK_RESETS, 1);
+            if (info >> 8) add64(s_acc, AG_ST_AXIS_ALIGNED, info >> 8);
+        }
+        rw = 0.0f; f = 0; ss.el_off[x] = -(t + 1);                               // scene_0.py:111-113
+    }
+    if (cold && A.diag != nullptr) add64(s_acc, AG_ST_COUNT + AG_DIAG_COLD_CALLS, 1);
+    ss.rw[x] = rw; ss.fl[x] = f;
+    ss.q1[x] = q1; ss.q2[x] = q2;
+    ss.thr[x] = (f != 0 || rw != 0.0f) ? __int_as_float(0x7f800000) : thr_clean;
+}
+
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
+// point = (1 - d*d/2) * (c, s) + d * (-s, c): the table entry's vector turned by the small angle d
+__device__ __forceinline__ float2 taylor_turn(float2 t, float d) {
+    const float u = fmaf(d * d, -0.5f, 1.0f);
+    const float2 ut = mul2(t, splat2(u));
+    return make_float2(fmaf(-d, t.y, ut.x), fmaf(d, t.x, ut.y));
+}
+
+// The directions in which link 1 (origin -> length l1) comes within `mg` of the closed square sq = (min_x, min_y, max_x,
+// max_y): the angular extent of (inflated square) n (disc of radius l1) seen from the origin.  That set is convex and,
+// unless the origin lies inside the inflated square, does not contain the origin, so its extent is spanned by its
+// vertices: corners inside the disc and circle / edge crossings (a ray from the centre is never tangent to the circle).
+// half < 0: never; half >= pi: always.
+__device__ void hazard_interval(float4 sq, double l1, double mg, float &mid, float &half) {
+    const double X0 = (double)sq.x - mg, Y0 = (double)sq.y - mg, X1 = (double)sq.z + mg, Y1 = (double)sq.w + mg;
+    if (X0 <= 0.0 && X1 >= 0.0 && Y0 <= 0.0 && Y1 >= 0.0) { mid = 0.0f; half = 4.0f; return; }
+    const double r2 = l1 * l1;
+    const double ref = atan2(0.5 * (Y0 + Y1), 0.5 * (X0 + X1));
+    double lo = 1.0e9, hi = -1.0e9;
+    auto take = [&](double px, double py) {
+        double a = atan2(py, px) - ref;
+        a -= TWO_PI * rint(a / TWO_PI);
+        lo = fmin(lo, a); hi = fmax(hi, a);
+    };
+    const double XS[2] = {X0, X1}, YS[2] = {Y0, Y1};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (XS[i] * XS[i] + YS[j] * YS[j] <= r2) take(XS[i], YS[j]);
+    for (int i = 0; i < 2; ++i) {
+        if (fabs(XS[i]) <= l1) {
+            const double y = sqrt(r2 - XS[i] * XS[i]);
+            if (y >= Y0 && y <= Y1) take(XS[i], y);
+            if (-y >= Y0 && -y <= Y1) take(XS[i], -y);
+        }
+        if (fabs(YS[i]) <= l1) {
+            const double xx = sqrt(r2 - YS[i] * YS[i]);
+            if (xx >= X0 && xx <= X1) take(xx, YS[i]);
+            if (-xx >= X0 && -xx <= X1) take(-xx, YS[i]);
+        }
+    }
+    if (hi < lo) { mid = 0.0f; half = -1.0f; return; }
+    mid = (float)(ref + 0.5 * (lo + hi));
+    half = (float)(0.5 * (hi - lo));
+}
+
+// Fill a table of n bins with (c, s) * len at the bin centres (b + 1/2) * 2pi/n, eight symmetric entries per
+// float64 sincospi.  hz != nullptr: bit 0 of .x is link 1's hazard bit (hz: [m][2] = (mid, half) intervals), else 0.
+__device__ void fill_table(float2 *lut, int n, double len, const float *hz, int m, bool all_hazard) {
+    const float hw = (float)(TWO_PI / (double)(2 * n)) + 2.0e-6f;                // half a bin + phase / float rounding
+    for (int i = threadIdx.x; i < n / 8; i += blockDim.x) {
+        double sd, cd;
+        sincospi((2.0 * i + 1.0) / (double)n, &sd, &cd);                         // angle (i + 1/2) * 2pi/n in (0, pi/4)
+        const float c = (float)(len * cd), s = (float)(len * sd);
+        const int q4 = n / 4;
+        const int bins[8] = {i, q4 - 1 - i, q4 + i, 2 * q4 - 1 - i, 2 * q4 + i, 3 * q4 - 1 - i, 3 * q4 + i, n - 1 - i};
+        const float xs[8] = {c, s, -s, -c, -c, -s, s, c};
+        const float ys[8] = {s, c, c, s, -s, -c, -c, -s};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int b = bins[j];
+            uint32_t bit = 0;
+            if (hz != nullptr) {
+                bit = all_hazard ? 1u : 0u;
+                const float th = ((float)b + 0.5f) * (float)(TWO_PI / (double)n);
+                for (int k = 0; k < m; ++k) {
+                    float dlt = th - hz[2 * k];
+                    dlt -= (float)TWO_PI * rintf(dlt * (float)(1.0 / TWO_PI));
+                    if (fabsf(dlt) <= hz[2 * k + 1] + hw) bit = 1u;
+                }
+            }
+            const float vx = hz != nullptr ? __uint_as_float((__float_as_uint(xs[j]) & ~1u) | bit) : xs[j];
+            lut[b] = make_float2(vx, ys[j]);
+        }
+    }
+}
+
+// The float32 arm from the tables (see the header of this file): elbow, half of link 2, link 1's hazard bit.
+struct TableArm { float2 ev, hv; uint32_t hazard; };
+__device__ __forceinline__ TableArm table_arm(double q1, double q2, double phase_scale, uint32_t lut1_a, uint32_t lut2_a) {
+    const uint32_t x1 = (uint32_t)__double2loint(fma(q1, phase_scale, PHASE_MAGIC));
+    const uint32_t x2 = (uint32_t)__double2loint(fma(q2, phase_scale, PHASE_MAGIC));
+    const float2 t1 = lds_f2(lut1_a + ((x1 >> (29 - B1)) & (uint32_t)((N1 - 1) << 3)));
+    const float2 t2 = lds_f2(lut2_a + ((x2 >> (29 - B2)) & (uint32_t)((N2 - 1) << 3)));
+    const float dA = fmaf(__uint_as_float((x1 & ((1u << (32 - B1)) - 1u)) | 0x4B000000u), RAD_PER_UNIT, C0_1);
+    const float dB = fmaf(__uint_as_float((x2 & ((1u << (32 - B2)) - 1u)) | 0x4B000000u), RAD_PER_UNIT, C0_2);
+    TableArm a;
+    a.ev = taylor_turn(t1, dA);
+    a.hv = taylor_turn(t2, dB);
+    a.hazard = __float_as_uint(t1.x) & 1u;
+    return a;
+}
+
+template <bool HAS_ACT, bool RECORD, bool M3>
+__global__ void __launch_bounds__(LB, AG_LUT_BLOCKS_PER_SM)
+k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G, const __grid_constant__ FastConst C,
+              const __grid_constant__ RolloutDev A, const __grid_constant__ LutConst L) {
+    extern __shared__ __align__(16) unsigned char smem_grid[];  // the staged grid (layout of stage_grid), then SlowShared
+    __shared__ __align__(16) float2 s_lut1[N1], s_lut2[N2];
+    __shared__ __align__(16) float2 s_ring[LW][RING][32];   // action rows t .. t+3 of each warp's tile (cp.async)
+    __shared__ FastList s_fl;
+    __shared__ float s_hz[2 * AG_LIST_MAX];
+    __shared__ unsigned long long s_acc[AG_ST_COUNT + AG_DIAG_COUNT];
+    __shared__ unsigned int s_done;
+    __shared__ int64_t s_tile[LW];                              // each warp's current tile
+    __shared__ int s_exits[LW];                                 // diagnostics: exits of the hot loop, per warp
+    SlowShared &ss = *reinterpret_cast<SlowShared *>(smem_grid + L.ss_off);     // dynamic: static shared memory is capped at 48 KB
+    if (threadIdx.x < AG_ST_COUNT + AG_DIAG_COUNT) s_acc[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_done = 0;
+    if (threadIdx.x < LW) s_exits[threadIdx.x] = 0;
+    {
+        const GridView V = stage_grid(G, A.env_id0, smem_grid);                  // one grid: block-uniform
+        build_fast_list(G, V, &s_fl);
+    }
+    // ---- the two tables
+    {
+        const int m = s_fl.m;
+        if ((int)threadIdx.x < m) hazard_interval(s_fl.sq[threadIdx.x], P.link_1, 2.0e-6, s_hz[2 * threadIdx.x], s_hz[2 * threadIdx.x + 1]);
+        __syncthreads();
+        fill_table(s_lut1, N1, P.link_1, s_hz, m < 0 ? 0 : m, m < 0 || (M3 && m > 3));   // no list / more squares than promised: all slow
+        fill_table(s_lut2, N2, 0.5 * P.link_2, nullptr, 0, false);
+    }
+    __syncthreads();
+
+    const int x = threadIdx.x, lane = x & 31;
+    const float INF = __int_as_float(0x7f800000);
+    const float2 zero2 = make_float2(0.f, 0.f);
+
+    for (;;) {
+        // ================================================================ draw a tile, global state -> SlowShared
+        {
+            int64_t tile = 0;
+            if (lane == 0) tile = (int64_t)atomicAdd(&g_tile_sched[2 * L.slot], 1u);
+            tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+            if (tile >= L.n_tiles) break;
+            if (lane == 0) s_tile[x >> 5] = tile;
+            const int64_t e = tile * 32 + lane;
+            const bool active = RECORD ? true : (e < A.n);                       // RECORD launches have complete tiles (zfill)
+            const int64_t ec = active ? e : A.n - 1;                             // inactive lanes shadow the last env, store nothing
+            ss.q1[x] = A.j1[ec]; ss.q2[x] = A.j2[ec];
+            const float rw0 = A.reward[ec];
+            const uint32_t fl0 = A.flags[ec];
+            ss.rw[x] = rw0; ss.fl[x] = fl0; ss.el_off[x] = (int)A.ep_len[ec];
+            const uint32_t rc0 = A.reset_ctr[ec];
+            ss.rc[x] = rc0;
+            const uint32_t sc0 = A.step_ctr[ec];
+            ss.sc0[x] = sc0;
+            if (active) A.step_ctr[e] = sc0 + (uint32_t)A.K;
+            float tx = C.tx, ty = C.ty;
+            if (A.targets != nullptr) {
+                const double2 tg = reinterpret_cast<const double2 *>(A.targets)[ec];
+                tx = (float)tg.x; ty = (float)tg.y;
+            }
+            ss.tx[x] = tx; ss.ty[x] = ty;
+            // a lane whose sticky state is not clean (flags / reward left by earlier step() calls) is slow until an
+            // episode end clears it: an infinite threshold makes its reach pre-test fire
+            ss.thr[x] = (fl0 != 0 || rw0 != 0.0f) ? INF : L.thr_c;
+            ss.t[x] = 0;
+            if (HAS_ACT) {                                                       // rows 0 .. RING-2 in flight
+                const uint32_t ring_lane = smem_u32(&s_ring[x >> 5][0][lane]);
+                const float2 *ap = reinterpret_cast<const float2 *>(A.actions) + e;
+#pragma unroll
+                for (int i = 0; i < RING - 1; ++i) {
+                    if (i < A.K && active) cp_async8(ring_lane + (uint32_t)(i << 8), ap);
+                    cp_async_commit();
+                    ap += A.row_stride;
+                }
+            }
+            if (RECORD && A.zfill) zero_fill_warp(A, tile * 32);
+            // the next valid reset pose, drawn by all lanes together
+            const PoseDraw pd = draw_valid_pose(P, G, C, smem_grid, &s_fl, rc0,
+                                                A.reset_u ? A.reset_u + ec * A.R * 2 : nullptr, A.R, A.seed,
+                                                (uint64_t)(A.env_id0 + ec));
+            ss.cq1[x] = pd.j1; ss.cq2[x] = pd.j2; ss.crc[x] = pd.rc; ss.cinfo[x] = pd.info;
+            __syncwarp();
+        }
+        for (;;) {   // ---- resume loop: one pass per entry into the hot loop (fresh tile, or after a level-2 call)
+        // ================================================================ set-up
+        // Everything the hot loop keeps in registers is (re)derived HERE from kernel parameters and shared memory -- for a
+        // fresh tile and again after every level-2 call.  A value live in a register across a call is spilled where it
+        // is defined and reloaded where it is used, i.e. inside the hot loop; this way nothing is live across a call.
+        // The asm statements keep the compiler from merging these values with copies computed before the call.
+        int64_t tile = s_tile[x >> 5];
+        asm volatile("" : "+l"(tile));
+        const int K = A.K;
+        const int64_t e = tile * 32 + lane;
+        const bool active = RECORD ? true : (e < A.n);
+        const uint64_t gid = (uint64_t)(A.env_id0 + (active ? e : A.n - 1));
+        const uint32_t sc0 = HAS_ACT ? 0u : ss.sc0[x];
+        // Table addresses: ptxas otherwise re-derives a shared-memory symbol's address (cluster rank << 24 | offset: S2UR
+        // + 4 uniform ops + 2 moves) at every use.  Row strides in bytes: otherwise re-read from the constant bank and
+        // re-shifted at every step.
+        uint32_t lut1_a, lut2_a, ring_lane;
+        asm volatile("mov.u32 %0, %1;" : "=r"(lut1_a) : "r"(smem_u32(s_lut1)));
+        asm volatile("mov.u32 %0, %1;" : "=r"(lut2_a) : "r"(smem_u32(s_lut2)));
+        asm volatile("mov.u32 %0, %1;" : "=r"(ring_lane) : "r"(smem_u32(&s_ring[x >> 5][0][lane])));
+        int64_t sa = A.row_stride * (int64_t)sizeof(float2), sr = A.row_stride * (int64_t)sizeof(float);
+        asm volatile("" : "+l"(sa));
+        asm volatile("" : "+l"(sr));
+        float hm = s_fl.hm;                                                      // side/2 + AG_M_BROAD (INF without a list)
+        asm volatile("" : "+f"(hm));
+        // square centres of the 3-obstacle map (occupancy_grid.py:45-47) live in registers
+        float2 o0, o1, o2;
+        if (M3) {
+            const float2 far = make_float2(1.0e9f, 1.0e9f);
+            o0 = s_fl.m > 0 ? s_fl.ctr[0] : far; o1 = s_fl.m > 1 ? s_fl.ctr[1] : far; o2 = s_fl.m > 2 ? s_fl.ctr[2] : far;
+        }
+        double q1 = ss.q1[x], q2 = ss.q2[x];
+        float thr = ss.thr[x];
+        const float tx = ss.tx[x], ty = ss.ty[x];
+        int t = ss.t[x];
+        char *p1 = reinterpret_cast<char *>(A.rec_j1 + e + (int64_t)t * A.row_stride);          // record row t
+        char *p2 = reinterpret_cast<char *>(A.rec_j2 + e + (int64_t)t * A.row_stride);
+        const char *pa = reinterpret_cast<const char *>(reinterpret_cast<const float2 *>(A.actions) + e + (int64_t)(t + RING - 1) * A.row_stride);   // next row to fetch
+
+        // what the last step leaves for level 1: the table arm, the box measures of link 2 (3-square form), the reach
+        // measure, link 1's hazard bit, angles in range
+        float l_ex = 0.f, l_ey = 0.f, l_gx = 0.f, l_gy = 0.f, l_s0 = 0.f, l_s1 = 0.f, l_s2 = 0.f, l_worst = 0.f;
+        bool l_haz = false, l_inr = false;
+        // one step up to the vote: true = this lane is slow
+        auto step = [&](float2 a, int t) -> bool {
+            double d1, d2;
+            if (HAS_ACT) {
+                d1 = (double)a.x; d2 = (double)a.y;
+            } else {
+                double u0, u1;
+                philox_uniform2(A.seed, gid, sc0 + (uint32_t)t, 0u, u0, u1);
+                d1 = __dmul_rn(__dsub_rn(u0, 0.5), P.action_scale);              // scene_0.py:84
+                d2 = __dmul_rn(__dsub_rn(u1, 0.5), P.action_scale);              // :85
+            }
+            q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);                      // two_joint_robot.py:71-72
+            const bool inr = (fabs(q1) < 1048576.0) && (fabs(q2) < 1048576.0);   // NaN-safe: NaN is slow
+            const TableArm ta = table_arm(q1, q2, L.phase_scale, lut1_a, lut2_a);
+            const float2 ev = ta.ev, hv = ta.hv;
+            const float c2x = ev.x + hv.x, c2y = ev.y + hv.y;                    // centre of link 2's box; half extents |hv|
+            const float gx = fmaf(2.0f, hv.x, ev.x), gy = fmaf(2.0f, hv.y, ev.y);
+            const float hx = fabsf(hv.x), hy = fabsf(hv.y);
+            float sep;
+            if (M3) {
+                const float s0 = fmaxf(fabsf(c2x - o0.x) - hx, fabsf(c2y - o0.y) - hy);
+                const float s1 = fmaxf(fabsf(c2x - o1.x) - hx, fabsf(c2y - o1.y) - hy);
+                const float s2 = fmaxf(fabsf(c2x - o2.x) - hx, fabsf(c2y - o2.y) - hy);
+                sep = fminf(fminf(s0, s1), s2);
+                l_s0 = s0; l_s1 = s1; l_s2 = s2;
+            } else {
+                sep = 1.0e30f;
+                const int m = s_fl.m;
+#pragma unroll 1
+                for (int k = 0; k < m; ++k) {
+                    const float2 o = s_fl.ctr[k];
+                    sep = fminf(sep, fmaxf(fabsf(c2x - o.x) - hx, fabsf(c2y - o.y) - hy));
+                }
+            }
+            const float worst = fmaxf(fabsf(tx - gx), fabsf(ty - gy));
+            l_ex = ev.x; l_ey = ev.y; l_gx = gx; l_gy = gy; l_worst = worst; l_haz = ta.hazard != 0; l_inr = inr;
+            if (RECORD) {                                                        // RECORD launches have complete tiles
+                __stcs(reinterpret_cast<float *>(p1), (float)q1);                // and zero-filled reward / flags planes
+                __stcs(reinterpret_cast<float *>(p2), (float)q2);
+                p1 += sr; p2 += sr;
+            }
+            // NaN-safe: an unordered comparison is slow.  Inactive lanes (ragged last tile, STATS mode only) are
+            // masked on the rare path.
+            return (ta.hazard != 0) || !(sep >= hm) || !(worst >= thr) || !inr;
+        };
+        // Ring slot of step t: ring_lane + (t mod RING) * 256.  Invariant at the top of the loop: rows t .. t+2 are in
+        // flight or landed in their slots, pa points at row t+3.
+        auto issue_row = [&](int row) {                                          // row `row` -> its slot, if it exists
+            if (HAS_ACT) {
+                if (row < K && active) cp_async8(ring_lane + (((uint32_t)row & (RING - 1)) << 8), pa);
+                cp_async_commit();
+                pa += sa;
+            }
+        };
+        auto fetch_row = [&](int t) -> float2 {                                  // this step's action, after its copy has landed
+            if (!HAS_ACT) return zero2;
+            cp_async_wait<RING - 1>();
+            return lds_f2(ring_lane + (((uint32_t)t & (RING - 1)) << 8));
+        };
+        bool need_level2 = false, event = false;
+        int cr = 0;
+        for (;;) {
+            bool slow = false;
+            // ---- hot loop: uneventful steps only; the warp leaves it when ANY lane is slow
+#pragma unroll 1
+            for (; t < K; ++t) {
+                issue_row(t + RING - 1);
+                slow = step(fetch_row(t), t);
+                if (__any_sync(0xFFFFFFFFu, slow)) break;
+            }
+            if (t >= K) break;
+            {
+
+            // Step t is recorded as uneventful.  Level 1 (no calls: the loop state stays in registers): the float32
+            // narrow phase of the slow lanes on the step's table arm; usually it clears them all.
+            cr = 0;
+            event = false;
+            if (slow && active) {
+                int c = 2, r = 2;
+                if (l_inr) {
+                    ArmF a;
+                    a.ex = l_ex; a.ey = l_ey; a.gx = l_gx; a.gy = l_gy;
+                    if (s_fl.m < 0) {
+                        c = 2;
+                    } else if (M3 && !l_haz) {                                   // the step's own measures name the pairs
+                        const uint32_t cand = (l_s0 < hm ? 2u : 0u) | (l_s1 < hm ? 8u : 0u) | (l_s2 < hm ? 32u : 0u);
+                        c = narrow_candidates(&s_fl, a, C, cand);
+                    } else {
+                        c = arm_fast_list(&s_fl, a, C, l_haz);
+                    }
+                    const float mr = AG_DELTA_P + 2.0e-7f;                       // reach_fast() on the step's measure
+                    r = l_worst > C.reach_eps + mr ? 0 : (l_worst < C.reach_eps - mr ? 1 : 2);
+                }
+                cr = c | (r << 2);
+                event = (cr != 0) || !(thr < INF);                               // a hit, target reached, undecided, or sticky state
+            }
+            if (A.diag != nullptr && lane == 0) s_exits[x >> 5] += 1;
+            // Reconverge HERE.  The vote below only makes the fragments of a diverged warp meet for one instruction
+            // (BRA.DIV + WARPSYNC.COLLECTIVE); without a real barrier the slow lanes and the others went back into
+            // the hot loop as separate fragments and every instruction of it was issued twice (profiles/r2d: 21 of 32
+            // threads per hot-loop instruction).
+            __syncwarp();
+            if (__any_sync(0xFFFFFFFFu, event)) { need_level2 = true; break; }
+            ++t;
+        }
+        }
+        if (!need_level2) {                                                      // the tile is finished: registers -> global
+            if (HAS_ACT) cp_async_wait<0>();
+            if (active) {
+                A.j1[e] = q1; A.j2[e] = q2; A.reward[e] = ss.rw[x]; A.flags[e] = (uint8_t)ss.fl[x];
+                A.ep_len[e] = (uint32_t)(ss.el_off[x] + K);
+                A.reset_ctr[e] = ss.rc[x];
+            }
+            const int n_act = __popc(__ballot_sync(0xFFFFFFFFu, active));
+            if (lane == 0) {
+                add64(s_acc, AG_ST_ENV_STEPS, (long long)n_act * K);
+                if (A.diag != nullptr) { add64(s_acc, AG_ST_COUNT + AG_DIAG_WARP_EXITS, s_exits[x >> 5]); s_exits[x >> 5] = 0; }
+            }
+            break;
+        }
+        // ================================================================ level 2 (out-of-line calls), then resume
+        ss.q1[x] = q1; ss.q2[x] = q2; ss.thr[x] = thr; ss.t[x] = t + 1; ss.cr[x] = event ? (cr | 16) : 0;
+        if (event) settle_step<RECORD>(P, G, C, A, ss, &s_fl, s_acc, smem_grid, L.thr_c, s_tile[x >> 5] * 32 + (threadIdx.x & 31));
+        __syncwarp();
+        }   // resume loop
+    }
+    // ---- no block barrier at the end (a warp that runs out of tiles just leaves): the last warp of the block
+    // flushes the block's counters, the last block of the grid re-arms the tile counters
+    __threadfence_block();
+    unsigned int prev = 0;
+    if (lane == 0) prev = atomicAdd(&s_done, 1u);
+    prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
+    if (prev == LW - 1) {
+        __threadfence_block();
+        if (lane < AG_ST_COUNT && A.stats != nullptr) {
+            const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(&s_acc[lane]);
+            if (v != 0) atomicAdd(&A.stats[lane], v);
+        }
+        if (A.diag != nullptr && lane < AG_DIAG_COUNT) {
+            const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(&s_acc[AG_ST_COUNT + lane]);
+            if (v != 0) atomicAdd(&A.diag[lane], v);
+        }
+        unsigned int *const sched = g_tile_sched + 2 * L.slot;
+        if (lane == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) {            // every block has drawn its last tile
+            sched[0] = 0; sched[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+int sm_slots(const void *kernel, size_t smem) {
+    int dev = 0, sms = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, LB, smem) != cudaSuccess) return 0;
+    return sms * occ;
+}
+
+template <bool HA, bool REC, bool M3>
+ag_status launch_t(const ag_params &P, const GridDev &G, const RolloutDev &A, const LutConst &L, size_t smem, cudaStream_t s) {
+    auto k = k_rollout_lut<HA, REC, M3>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (ag_status)e;
+    const int slots = sm_slots(reinterpret_cast<const void *>(k), smem);
+    if (slots <= 0) return (ag_status)cudaGetLastError();
+    const int64_t want = (L.n_tiles + LW - 1) / LW;
+    const unsigned blocks = (unsigned)(want < slots ? want : slots);
+    k<<<blocks, LB, smem, s>>>(P, G, make_fast_const(P, G), A, L);
+    ag_note_launch();
+    return (ag_status)cudaGetLastError();
+}
+
+}  // namespace
+
+// The persistent kernel serves the FAST engine on one staged small sparse grid (obstacle list), cartesian target.
+bool rollout_lut_applies(const ag_params &P, const GridDev &G, const RolloutDev &A) {
+    static const bool legacy = std::getenv("AG_ROLLOUT_LEGACY") != nullptr;
+    const bool rec = A.rec_j1 != nullptr;   // RECORD: complete tiles and zero-filled reward / flags planes only
+    // the table arm's error (2.2e-7 m per metre of link 1, 2.8e-7 per metre of link 2, 5e-8 of rounding) must stay
+    // inside the float32 filter's budget AG_DELTA_P
+    const bool budget = 2.2e-7 * P.link_1 + 2.8e-7 * P.link_2 + 5.0e-8 <= (double)AG_DELTA_P;
+    return !legacy && G.stage && G.n_grids == 1 && G.S <= 32 && !P.choose_j_tar && (!rec || A.zfill) && budget;
+}
+
+ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem_grid, cudaStream_t s) {
+    LutConst L;
+    L.phase_scale = 4294967296.0 / TWO_PI;
+    L.thr_c = (float)P.reach_eps + (AG_DELTA_P + 2.0e-7f);
+    L.n_tiles = (A.n + 31) / 32;
+    static std::atomic<unsigned> next_slot{0};
+    L.slot = next_slot.fetch_add(1, std::memory_order_relaxed) % AG_TILE_SLOTS;
+    L.ss_off = (uint32_t)((smem_grid + 15) & ~(size_t)15);
+    const size_t smem = (size_t)L.ss_off + sizeof(SlowShared);
+    const bool ha = A.actions != nullptr, rec = A.rec_j1 != nullptr;
+    // the unrolled form tests three squares (scene_0's map); fewer are padded with far-away ones in the kernel
+    const bool m3 = A.max_occupied >= 0 && A.max_occupied <= 3;
+#define AG_LUT(HA, REC) (m3 ? launch_t<HA, REC, true>(P, G, A, L, smem, s) : launch_t<HA, REC, false>(P, G, A, L, smem, s))
+    if (ha) return rec ? AG_LUT(true, true) : AG_LUT(true, false);
+    return rec ? AG_LUT(false, true) : AG_LUT(false, false);
+#undef AG_LUT
+}

@@ -204,7 +204,7 @@ class BatchedScene:
         self._reset(mask, reset_u, False)
 
     # ---- K4 ------------------------------------------------------------------------------------
-    def _rollout_args(self, K, actions, reset_u, rec, engine):
+    def _rollout_args(self, K, actions, reset_u, rec, engine, targets=None, diag=True):
         a = _lib.RolloutArgs()
         a.n, a.env_id0, a.K = self.n, self.env_id0, int(K)
         a.engine = self.engine if engine is None else _engine(engine)
@@ -221,7 +221,8 @@ class BatchedScene:
             a.rec_reward = rec["reward"].data_ptr() if rec.get("reward") is not None else None
             a.rec_flags = rec["flags"].data_ptr()
         a.stats = self.stats.data_ptr()
-        a.diag = self.diag.data_ptr()
+        a.diag = self.diag.data_ptr() if diag else None
+        a.targets = None if targets is None else targets.data_ptr()
         return a
 
     def alloc_records(self, K, pinned_host=False, reward=True):
@@ -245,7 +246,7 @@ class BatchedScene:
         out[(f & _lib.FLAG_DONE) != 0] = float(p.reward_reach)
         return out
 
-    def rollout(self, K, actions=None, reset_u=None, record=True, out=None, engine=None):
+    def rollout(self, K, actions=None, reset_u=None, record=True, out=None, engine=None, targets=None, diag=True):
         """The loop body of experiment/experiment_0.py:20-34, K times, in ONE kernel:
         action -> step -> record -> reset when done or collision.
 
@@ -255,6 +256,9 @@ class BatchedScene:
         record : write (joint_1, joint_2, step_reward, flags) per step into `out`
                  (dict of [K,N] tensors from alloc_records) -- post-step, pre-reset, like the reference's
                  record.append.  Episode statistics always accumulate into self.stats.
+        targets: optional [N,2] float64 per-env cartesian targets replacing target_c in the reach test
+                 (scene_0.py:129-130); ignored in joint-target mode.
+        diag   : accumulate the FAST-filter diagnostics into self.diag (a few shared-memory atomics per warp exit).
         """
         if actions is not None:
             actions = torch.as_tensor(actions, device=self.device)
@@ -266,7 +270,9 @@ class BatchedScene:
         rec = None
         if record:
             rec = out if out is not None else self.alloc_records(K)
-        a = self._rollout_args(K, actions, reset_u, rec, engine)
+        if targets is not None:
+            targets = as_f64(targets, self.device).reshape(self.n, 2).contiguous()
+        a = self._rollout_args(K, actions, reset_u, rec, engine, targets, diag)
         g = self.grid.c_struct()
         _lib.check(self._lib.ag_rollout(self.params(), g, C.byref(a), stream_ptr(self.device)), "ag_rollout")
         return rec

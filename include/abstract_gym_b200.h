@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AG_ABI_VERSION 2
+#define AG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define AG_API __attribute__((visibility("default")))
@@ -209,6 +209,8 @@ typedef struct ag_rollout_args {
     uint8_t *rec_flags;
     int64_t *stats;
     int64_t *diag;           /* optional int64[AG_DIAG_COUNT] filter diagnostics (accumulated), or NULL */
+    const double *targets;   /* optional [n][2] float64 per-env cartesian targets replacing Scene.target_c in the reach
+                              * test (scenario/scene_0.py:129-130), or NULL = p->target_x/y; ignored in joint-target mode */
 } ag_rollout_args;
 
 AG_API ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream);
