@@ -12,6 +12,9 @@ using namespace agd;
 // ag_rollout_lut.cu: the persistent kernel for scene_0-class grids (obstacle list, one grid, cartesian target)
 bool rollout_lut_applies(const ag_params &P, const GridDev &G, const RolloutDev &A);
 ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s);
+// ag_dense.cu: the warp-cooperative kernel for grids that go through the cell traversal (needs the transposed planes)
+bool rollout_coop_applies(const ag_params &P, const GridDev &G, const RolloutDev &A);
+ag_status launch_rollout_coop(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s);
 
 namespace {
 
@@ -735,6 +738,7 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
         const bool list = G.stage && g->S <= 32 && g->max_occupied >= 0 && g->max_occupied <= AG_LIST_MAX;
         if (list && rollout_lut_applies(*p, G, A)) return launch_rollout_lut(*p, G, A, smem, s);
         if (list) return launch_rollout_e<AG_ENGINE_FAST, BP_LIST>(*p, G, A, smem, s);
+        if (rollout_coop_applies(*p, G, A)) return launch_rollout_coop(*p, G, A, smem, s);
         return launch_rollout_e<AG_ENGINE_FAST, BP_TRAVERSAL>(*p, G, A, smem, s);
     }
     if (a->engine == AG_ENGINE_EXACT) return launch_rollout_e<AG_ENGINE_EXACT, BP_ANY>(*p, G, A, smem, s);

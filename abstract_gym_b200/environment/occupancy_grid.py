@@ -200,9 +200,19 @@ class BatchedOccupancyGrid:
 
     @classmethod
     def random(cls, n_grids, size, obstacle_probability, envs_per_grid, environment_size=1.6, device=None,
-               generator=None):
+               generator=None, clear_base_cells=0):
+        """i.i.d. Bernoulli(obstacle_probability) maps (occupancy_grid.py:35-36 for every grid).  clear_base_cells = k > 0
+        frees the (2k) x (2k) cells around the arm's base at the origin: a map whose base cell is occupied has no free
+        pose at all (the reference's random_valid_pose would never return, scene_0.py:179)."""
         dev = require_cuda(device)
         occ = torch.rand(n_grids, size, size, device=dev, generator=generator) < obstacle_probability
+        k = int(clear_base_cells)
+        if k > 0:
+            # the origin is the corner shared by cells (row, col) = (S/2 - 1 .. S/2 + 1 ...): x = c*side - E/2 = 0 at
+            # c = (S-1)/2, y = E/2 - r*side = 0 at r = (S-1)/2 (occupancy_grid.py:59-67)
+            mid = (size - 1) / 2.0
+            lo, hi = int(np.floor(mid)) - k + 1, int(np.ceil(mid)) + k
+            occ[:, max(lo, 0):hi + 1, max(lo - 1, 0):hi] = False
         return cls(occ, envs_per_grid, environment_size, dev)
 
     @classmethod

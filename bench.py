@@ -227,7 +227,8 @@ def run_ours(args, rank, world, local):
         grid.load_from_matrix((np.random.default_rng(4).random((1024, 1024)) < 0.002).astype(np.uint8))
     else:
         ggen = torch.Generator(device=dev).manual_seed(5)     # same maps on every rank; envs pick them by global id
-        grid = ag.BatchedOccupancyGrid.random(max(1, world * n // 256), 256, 0.008, 256, device=dev, generator=ggen)
+        grid = ag.BatchedOccupancyGrid.random(max(1, world * n // 256), 256, 0.008, 256, device=dev, generator=ggen,
+                                              clear_base_cells=2)
     robot = ag.BatchedTwoJointRobot.random(n, device=dev, generator=gen)
     scene = ag.BatchedScene(robot, grid, engine=args.engine, seed=0, env_id0=lo)
     scene.random_valid_pose()                        # experiment_0.py:16
