@@ -11,7 +11,7 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 ENGINE_EXACT, ENGINE_FAST, ENGINE_BRUTE = 0, 1, 2
 ENGINES = {"exact": ENGINE_EXACT, "fast": ENGINE_FAST, "brute": ENGINE_BRUTE}
 FLAG_COLLISION, FLAG_DONE = 1, 2
@@ -55,7 +55,9 @@ class RolloutArgs(C.Structure):
                 ("j1", C.c_void_p), ("j2", C.c_void_p), ("reward", C.c_void_p), ("flags", C.c_void_p),
                 ("step_ctr", C.c_void_p), ("reset_ctr", C.c_void_p), ("ep_len", C.c_void_p),
                 ("rec_j1", C.c_void_p), ("rec_j2", C.c_void_p), ("rec_reward", C.c_void_p),
-                ("rec_flags", C.c_void_p), ("stats", C.c_void_p), ("diag", C.c_void_p), ("targets", C.c_void_p)]
+                ("rec_flags", C.c_void_p), ("stats", C.c_void_p), ("diag", C.c_void_p), ("targets", C.c_void_p),
+                ("events", C.c_void_p), ("event_count", C.c_void_p), ("event_capacity", C.c_int64),
+                ("event_step0", C.c_int32), ("reserved2", C.c_int32)]
 
 
 # every symbol include/abstract_gym_b200.h declares: (restype, argtypes)
@@ -80,7 +82,7 @@ SYMBOLS = {
                         _vp, _i64, _i64, _i32, _vp]),
     "ag_rollout": (_i32, [C.POINTER(Params), C.POINTER(Grid), C.POINTER(RolloutArgs), _vp]),
     "ag_launch_count": (_i64, []),
-    "ag_pipeline_create": (_i32, [C.POINTER(_vp), _i32, _i64, _i32, _i64, _i32, _i32]),
+    "ag_pipeline_create": (_i32, [C.POINTER(_vp), _i32, _i64, _i32, _i64, _i32, _i32, _i64]),
     "ag_pipeline_destroy": (None, [_vp]),
     "ag_rollout_host": (_i32, [_vp, C.POINTER(Params), C.POINTER(Grid), C.POINTER(RolloutArgs), _vp]),
 }
@@ -101,10 +103,9 @@ def load():
     if not os.path.exists(path) or _build.needs_build():
         try:
             _build.build()
-        except Exception as e:  # a stale-but-present library is still usable; a missing one is fatal
-            if not os.path.exists(path):
-                raise ImportError("abstract_gym_b200: the CUDA extension %s is missing and could not be built "
-                                  "(%s). There is no CPU fallback." % (path, e)) from e
+        except Exception as e:  # never run a stale binary silently: the sources are newer than the library
+            raise ImportError("abstract_gym_b200: the CUDA extension %s is %s and could not be built (%s). "
+                              "There is no CPU fallback." % (path, "stale" if os.path.exists(path) else "missing", e)) from e
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol

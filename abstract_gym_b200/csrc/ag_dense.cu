@@ -295,6 +295,7 @@ k_rollout_coop(const __grid_constant__ ag_params P, const __grid_constant__ Grid
                 if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
                 if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
                 store_record<RECORD>(A, (int64_t)t * A.row_stride + e, q1, q2, rw, fl);    // experiment_0.py:23-25
+                emit_event(A, e, t, rw, fl);
                 ++el; ++t;
                 if (fl) {                                                        // experiment_0.py:30-34
                     ++loc[AG_ST_EPISODES];

@@ -91,22 +91,35 @@ struct ag_pipeline {
     uint8_t *d_fl[NSTAGE];
     int64_t *d_stats;      // [NSTAGE][AG_ST_COUNT]
     int64_t *h_stats;      // pinned
+    int64_t event_cap;     // event sink of one call (all slices append to it)
+    uint32_t *d_events;
+    int64_t *d_evcount;
+    int64_t *h_evcount;    // pinned
 };
+
+namespace {
+
+// the caller's current device, restored on scope exit (single-process multi-GPU callers)
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+void pipeline_sync(ag_pipeline *pl) {
+    for (int s = 0; s < ag_pipeline::NSTAGE; ++s)
+        if (pl->st[s]) cudaStreamSynchronize(pl->st[s]);
+}
+
+}  // namespace
 
 #define AG_CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (ag_status)e_; } while (0)
 
-ag_status ag_pipeline_create(ag_pipeline **out, int32_t device, int64_t n, int32_t K, int64_t chunk_envs,
-                             int32_t chunk_steps, int32_t record) {
-    if (!out) return AG_ERR_NULL;
-    if (n < 1 || K < 1 || (chunk_steps <= 0 && chunk_envs < 1)) return AG_ERR_SHAPE;
-    AG_CU(cudaSetDevice(device));
-    ag_pipeline *pl = new (std::nothrow) ag_pipeline();
-    if (!pl) return (ag_status)cudaErrorMemoryAllocation;
-    std::memset(pl, 0, sizeof(*pl));
-    pl->device = device; pl->n = n; pl->K = K; pl->record = record;
-    pl->chunk_steps = chunk_steps > 0 ? (chunk_steps < K ? chunk_steps : K) : 0;
-    pl->chunk = chunk_envs < n ? chunk_envs : n;
-    pl->chunk = (pl->chunk + 255) & ~(int64_t)255;     // block-aligned chunks keep env->grid maps uniform
+static ag_status pipeline_alloc(ag_pipeline *pl, int64_t n, int32_t K, int32_t record, int64_t event_capacity) {
     const size_t ck = pl->chunk_steps > 0 ? (size_t)n * pl->chunk_steps : (size_t)pl->chunk * K;
     for (int s = 0; s < ag_pipeline::NSTAGE; ++s) {
         AG_CU(cudaStreamCreateWithFlags(&pl->st[s], cudaStreamNonBlocking));
@@ -121,13 +134,41 @@ ag_status ag_pipeline_create(ag_pipeline **out, int32_t device, int64_t n, int32
     }
     AG_CU(cudaMalloc(&pl->d_stats, sizeof(int64_t) * AG_ST_COUNT * ag_pipeline::NSTAGE));
     AG_CU(cudaMallocHost(&pl->h_stats, sizeof(int64_t) * AG_ST_COUNT * ag_pipeline::NSTAGE));
+    if (event_capacity > 0) {
+        AG_CU(cudaMalloc(&pl->d_events, (size_t)event_capacity * 3 * sizeof(uint32_t)));
+        AG_CU(cudaMalloc(&pl->d_evcount, sizeof(int64_t)));
+        AG_CU(cudaMallocHost(&pl->h_evcount, sizeof(int64_t)));
+    }
+    return AG_OK;
+}
+
+ag_status ag_pipeline_create(ag_pipeline **out, int32_t device, int64_t n, int32_t K, int64_t chunk_envs,
+                             int32_t chunk_steps, int32_t record, int64_t event_capacity) {
+    if (!out) return AG_ERR_NULL;
+    *out = nullptr;
+    if (n < 1 || K < 1 || (chunk_steps <= 0 && chunk_envs < 1) || event_capacity < 0) return AG_ERR_SHAPE;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return (ag_status)guard.err;
+    ag_pipeline *pl = new (std::nothrow) ag_pipeline();
+    if (!pl) return (ag_status)cudaErrorMemoryAllocation;
+    std::memset(pl, 0, sizeof(*pl));
+    pl->device = device; pl->n = n; pl->K = K; pl->record = record;
+    pl->chunk_steps = chunk_steps > 0 ? (chunk_steps < K ? chunk_steps : K) : 0;
+    pl->chunk = chunk_envs < n ? chunk_envs : n;
+    pl->chunk = (pl->chunk + 255) & ~(int64_t)255;     // block-aligned chunks keep env->grid maps uniform
+    pl->event_cap = event_capacity;
+    const ag_status st = pipeline_alloc(pl, n, K, record, event_capacity);
+    if (st != AG_OK) {                                 // free whatever was created before the failure
+        ag_pipeline_destroy(pl);
+        return st;
+    }
     *out = pl;
     return AG_OK;
 }
 
 void ag_pipeline_destroy(ag_pipeline *pl) {
     if (!pl) return;
-    cudaSetDevice(pl->device);
+    DeviceGuard guard(pl->device);
     for (int s = 0; s < ag_pipeline::NSTAGE; ++s) {
         if (pl->st[s]) { cudaStreamSynchronize(pl->st[s]); cudaStreamDestroy(pl->st[s]); }
         if (pl->ev[s]) cudaEventDestroy(pl->ev[s]);
@@ -135,21 +176,36 @@ void ag_pipeline_destroy(ag_pipeline *pl) {
     }
     cudaFree(pl->d_stats);
     cudaFreeHost(pl->h_stats);
+    cudaFree(pl->d_events); cudaFree(pl->d_evcount);
+    cudaFreeHost(pl->h_evcount);
     delete pl;
 }
 
-// chunk i: [stream i%3]  H2D actions (strided rows) -> K4 -> D2H records (strided rows).
-// Copies of chunk i+1 overlap the kernel of chunk i and the read-back of chunk i-1.
-ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g, const ag_rollout_args *a,
-                          int64_t *stats_host) {
-    if (!pl || !p || !g || !a) return AG_ERR_NULL;
-    if (a->n != pl->n || a->K != pl->K) return AG_ERR_SHAPE;
+// chunk i: [stream i%3]  H2D actions -> K4 -> D2H records.  Copies of chunk i+1 overlap the kernel of chunk i and the
+// read-back of chunk i-1.
+static ag_status rollout_host_impl(ag_pipeline *pl, const ag_params *p, const ag_grid *g, const ag_rollout_args *a) {
     const bool rec = a->rec_j1 != nullptr;
-    if (rec && !pl->record) return AG_ERR_MODE;
-    AG_CU(cudaSetDevice(pl->device));
+    const bool want_events = a->events != nullptr;
     const int64_t n = a->n, K = a->K;
     for (int s = 0; s < ag_pipeline::NSTAGE; ++s)
         AG_CU(cudaMemsetAsync(pl->d_stats + s * AG_ST_COUNT, 0, sizeof(int64_t) * AG_ST_COUNT, pl->st[s]));
+    if (want_events) {
+        AG_CU(cudaMemsetAsync(pl->d_evcount, 0, sizeof(int64_t), pl->st[0]));
+        AG_CU(cudaEventRecord(pl->ev[0], pl->st[0]));
+        for (int s = 1; s < ag_pipeline::NSTAGE; ++s) AG_CU(cudaStreamWaitEvent(pl->st[s], pl->ev[0], 0));
+    }
+    auto stage_args = [&](ag_rollout_args &b, int s) {
+        b.stats = pl->d_stats + s * AG_ST_COUNT;
+        if (rec) {
+            b.rec_j1 = pl->d_j1[s]; b.rec_j2 = pl->d_j2[s];
+            b.rec_reward = a->rec_reward ? pl->d_rw[s] : nullptr;      // planes the caller does not want are not written
+            b.rec_flags = a->rec_flags ? pl->d_fl[s] : nullptr;
+            if (b.rec_flags && !b.rec_reward) b.rec_reward = pl->d_rw[s];   // compact records: the reward plane stays on the device
+        }
+        b.events = want_events ? pl->d_events : nullptr;
+        b.event_count = want_events ? pl->d_evcount : nullptr;
+        b.event_capacity = pl->event_cap;
+    };
     if (pl->chunk_steps > 0) {
         // Slices of consecutive STEPS over all envs: every copy is one contiguous block (rows t0..t0+k of
         // the [K][n] arrays), which PCIe moves ~7 % faster than the pitched 2-D copies of env slices.  The
@@ -162,12 +218,12 @@ ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g,
             cudaStream_t cs = pl->st[s];
             ag_rollout_args b = *a;
             b.K = (int32_t)k;
-            b.stats = pl->d_stats + s * AG_ST_COUNT;
+            b.event_step0 = a->event_step0 + (int32_t)t0;
+            stage_args(b, s);
             if (a->actions) {
                 AG_CU(cudaMemcpyAsync(pl->d_act[s], a->actions + t0 * n * 2, (size_t)k * n * 8, cudaMemcpyHostToDevice, cs));
                 b.actions = pl->d_act[s];
             }
-            if (rec) { b.rec_j1 = pl->d_j1[s]; b.rec_j2 = pl->d_j2[s]; b.rec_reward = pl->d_rw[s]; b.rec_flags = pl->d_fl[s]; }
             if (i > 0) AG_CU(cudaStreamWaitEvent(cs, pl->ev[(i - 1) % ag_pipeline::NSTAGE], 0));
             ag_status st = ag_rollout_impl(p, g, &b, n, cs);
             if (st) return st;
@@ -177,7 +233,8 @@ ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g,
                 AG_CU(cudaMemcpyAsync(a->rec_j2 + t0 * n, pl->d_j2[s], (size_t)k * n * 4, cudaMemcpyDeviceToHost, cs));
                 if (a->rec_reward)
                     AG_CU(cudaMemcpyAsync(a->rec_reward + t0 * n, pl->d_rw[s], (size_t)k * n * 4, cudaMemcpyDeviceToHost, cs));
-                AG_CU(cudaMemcpyAsync(a->rec_flags + t0 * n, pl->d_fl[s], (size_t)k * n, cudaMemcpyDeviceToHost, cs));
+                if (a->rec_flags)
+                    AG_CU(cudaMemcpyAsync(a->rec_flags + t0 * n, pl->d_fl[s], (size_t)k * n, cudaMemcpyDeviceToHost, cs));
             }
         }
     }
@@ -191,13 +248,14 @@ ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g,
         b.j1 = a->j1 + c0; b.j2 = a->j2 + c0; b.reward = a->reward + c0; b.flags = a->flags + c0;
         b.step_ctr = a->step_ctr + c0; b.reset_ctr = a->reset_ctr + c0; b.ep_len = a->ep_len + c0;
         b.reset_u = a->reset_u ? a->reset_u + c0 * a->R * 2 : nullptr;
-        b.stats = pl->d_stats + s * AG_ST_COUNT;
+        b.targets = a->targets ? a->targets + c0 * 2 : nullptr;
+        if (want_events) return AG_ERR_MODE;           // the event sink numbers envs per launch: step slices only
+        stage_args(b, s);
         if (a->actions) {
             AG_CU(cudaMemcpy2DAsync(pl->d_act[s], (size_t)pl->chunk * 8, a->actions + c0 * 2, (size_t)n * 8,
                                     (size_t)cn * 8, (size_t)K, cudaMemcpyHostToDevice, cs));
             b.actions = pl->d_act[s];
         }
-        if (rec) { b.rec_j1 = pl->d_j1[s]; b.rec_j2 = pl->d_j2[s]; b.rec_reward = pl->d_rw[s]; b.rec_flags = pl->d_fl[s]; }
         ag_status st = ag_rollout_impl(p, g, &b, pl->chunk, cs);
         if (st) return st;
         if (rec) {
@@ -208,14 +266,43 @@ ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g,
             if (a->rec_reward)   // optional on the host side: reward is a function of flags (DESIGN.md "compact records")
                 AG_CU(cudaMemcpy2DAsync(a->rec_reward + c0, (size_t)n * 4, pl->d_rw[s], (size_t)pl->chunk * 4,
                                         (size_t)cn * 4, (size_t)K, cudaMemcpyDeviceToHost, cs));
-            AG_CU(cudaMemcpy2DAsync(a->rec_flags + c0, (size_t)n, pl->d_fl[s], (size_t)pl->chunk, (size_t)cn,
-                                    (size_t)K, cudaMemcpyDeviceToHost, cs));
+            if (a->rec_flags)
+                AG_CU(cudaMemcpy2DAsync(a->rec_flags + c0, (size_t)n, pl->d_fl[s], (size_t)pl->chunk, (size_t)cn,
+                                        (size_t)K, cudaMemcpyDeviceToHost, cs));
         }
     }
     for (int s = 0; s < ag_pipeline::NSTAGE; ++s)
         AG_CU(cudaMemcpyAsync(pl->h_stats + s * AG_ST_COUNT, pl->d_stats + s * AG_ST_COUNT,
                               sizeof(int64_t) * AG_ST_COUNT, cudaMemcpyDeviceToHost, pl->st[s]));
     for (int s = 0; s < ag_pipeline::NSTAGE; ++s) AG_CU(cudaStreamSynchronize(pl->st[s]));
+    if (want_events) {                                 // every kernel is done: the count, then exactly that many events
+        AG_CU(cudaMemcpyAsync(pl->h_evcount, pl->d_evcount, sizeof(int64_t), cudaMemcpyDeviceToHost, pl->st[0]));
+        AG_CU(cudaStreamSynchronize(pl->st[0]));
+        const int64_t cnt = *pl->h_evcount, stored = cnt < pl->event_cap ? cnt : pl->event_cap;
+        if (stored > 0)
+            AG_CU(cudaMemcpyAsync(a->events, pl->d_events, (size_t)stored * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, pl->st[0]));
+        AG_CU(cudaStreamSynchronize(pl->st[0]));
+        *a->event_count = cnt;
+    }
+    return AG_OK;
+}
+
+ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g, const ag_rollout_args *a,
+                          int64_t *stats_host) {
+    if (!pl || !p || !g || !a) return AG_ERR_NULL;
+    if (a->n != pl->n || a->K != pl->K) return AG_ERR_SHAPE;
+    const int njoint = (a->rec_j1 != nullptr) + (a->rec_j2 != nullptr);
+    if (njoint == 1 || (njoint == 0 && (a->rec_reward || a->rec_flags))) return AG_ERR_NULL;   // joints: both or none
+    if (a->rec_reward && !a->rec_flags) return AG_ERR_NULL;
+    if (njoint == 2 && !pl->record) return AG_ERR_MODE;
+    if (a->events && (!a->event_count || pl->event_cap <= 0)) return AG_ERR_MODE;
+    DeviceGuard guard(pl->device);
+    if (guard.err != cudaSuccess) return (ag_status)guard.err;
+    const ag_status st = rollout_host_impl(pl, p, g, a);
+    if (st != AG_OK) {                                 // nothing may still be writing the caller's buffers
+        pipeline_sync(pl);
+        return st;
+    }
     if (stats_host)
         for (int k = 0; k < AG_ST_COUNT; ++k)
             for (int s = 0; s < ag_pipeline::NSTAGE; ++s) stats_host[k] += pl->h_stats[s * AG_ST_COUNT + k];

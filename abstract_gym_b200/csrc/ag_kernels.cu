@@ -284,6 +284,7 @@ __device__ __noinline__ void cold_section(const ag_params &P, const GridDev &G, 
         if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
         if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
         store_record<RECORD>(A, hs.o[x], q1, q2, rw, fl);                         // experiment_0.py:23-25
+        emit_event(A, e, t, rw, fl);
     }
     if (d >> 2) acc32(s_acc, AG_ST_AXIS_ALIGNED, d >> 2);
     if (fl) {                                                                     // experiment_0.py:30-34
@@ -453,8 +454,10 @@ k_rollout(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G
                     if (!undecided) {
                         if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
                         if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
-                        if (!LIST || fl != 0 || rw != 0.0f)                                        // else: already recorded
+                        if (!LIST || fl != 0 || rw != 0.0f) {                                      // else: already recorded
                             store_record<RECORD>(A, o, q1, q2, rw, fl);                            // experiment_0.py:23-25
+                            emit_event(A, e0, t, rw, fl);
+                        }
                         event = (fl | (d >> 2)) != 0;
                         reach_thr = (rw != 0.0f) ? __int_as_float(0x7f800000) : reach_thr_clean;
                     }
@@ -559,6 +562,7 @@ k_rollout_async(const __grid_constant__ ag_params P, const __grid_constant__ Gri
                 if (d & 1) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }   // scene_0.py:95-97
                 if (d & 2) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }            // :98-100
                 store_record<RECORD>(A, (int64_t)t * A.row_stride + e, q1, q2, rw, fl);    // experiment_0.py:23-25
+                emit_event(A, e, t, rw, fl);
                 ++el; ++t;
                 if (fl) {                                                        // experiment_0.py:30-34
                     ++loc[AG_ST_EPISODES];
@@ -711,7 +715,9 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
     if (!a->j1 || !a->j2 || !a->reward || !a->flags || !a->step_ctr || !a->reset_ctr || !a->ep_len || !a->stats)
         return AG_ERR_NULL;
     const int nrec = (a->rec_j1 != nullptr) + (a->rec_j2 != nullptr) + (a->rec_reward != nullptr) + (a->rec_flags != nullptr);
-    if (nrec != 0 && nrec != 4) return AG_ERR_NULL;
+    const bool joints_only = nrec == 2 && a->rec_j1 != nullptr && a->rec_j2 != nullptr;
+    if (nrec != 0 && nrec != 4 && !joints_only) return AG_ERR_NULL;
+    if (a->events != nullptr && (a->event_count == nullptr || a->event_capacity < 0)) return AG_ERR_NULL;
     if (a->reset_u && a->R < 1) return AG_ERR_SHAPE;
     if (((uintptr_t)a->actions % 8) || ((uintptr_t)a->reset_u % 16) || ((uintptr_t)a->targets % 16)) return AG_ERR_ALIGN;
     if (row_stride < a->n) return AG_ERR_SHAPE;
@@ -731,6 +737,9 @@ ag_status ag_rollout_impl(const ag_params *p, const ag_grid *g, const ag_rollout
     // warp-wide 16-byte zero fill of the reward / flags record planes needs 16-byte aligned rows
     A.zfill = (a->rec_reward != nullptr && a->n % 32 == 0 && row_stride % 16 == 0 &&
                (uintptr_t)a->rec_reward % 16 == 0 && (uintptr_t)a->rec_flags % 16 == 0) ? 1 : 0;
+    if (joints_only && a->n % 32 == 0) A.zfill = 1;      // nothing to fill: the uneventful step writes its joints only
+    A.events = a->events; A.event_count = reinterpret_cast<unsigned long long *>(a->event_count);
+    A.event_cap = a->event_capacity; A.event_step0 = a->event_step0;
     cudaStream_t s = (cudaStream_t)stream;
     // FAST engine: the obstacle-list broad phase when the caller vouches for small sparse staged grids
     // (ag_grid.max_occupied); a block whose grid turns out not to qualify falls back to EXACT per lane.

@@ -27,7 +27,23 @@ struct RolloutDev {
     int32_t zfill;            // 1: the reward / flags planes of this launch are zero-filled up front by each warp
     int32_t max_occupied;     // ag_grid.max_occupied (hint: upper bound on occupied cells)
     const double *targets;    // optional per-env cartesian targets [n][2], or nullptr
+    uint32_t *events;         // optional event sink (ag_rollout_args.events), or nullptr
+    unsigned long long *event_count;
+    int64_t event_cap;
+    int32_t event_step0;
 };
+
+// one eventful step -> the event sink (ag_rollout_args.events): (local env, step << 8 | flags, reward bits)
+__device__ __forceinline__ void emit_event(const RolloutDev &A, int64_t e, int t, float rw, uint32_t fl) {
+    if (A.events != nullptr && (fl != 0 || rw != 0.0f)) {
+        const unsigned long long i = atomicAdd(A.event_count, 1ull);
+        if (i < (unsigned long long)A.event_cap) {
+            A.events[3 * i] = (uint32_t)e;
+            A.events[3 * i + 1] = ((uint32_t)(A.event_step0 + t) << 8) | (fl & 0xFFu);
+            A.events[3 * i + 2] = __float_as_uint(rw);
+        }
+    }
+}
 
 // ------------------------------------------------------------------------- per-block context
 // Every kernel that reads the grid starts the same way: stage the block's grid into shared memory
@@ -144,8 +160,10 @@ __device__ __forceinline__ void store_record(const RolloutDev &A, int64_t o, dou
     if (RECORD) {
         __stcs(A.rec_j1 + o, (float)q1);
         __stcs(A.rec_j2 + o, (float)q2);
-        __stcs(A.rec_reward + o, rw);
-        A.rec_flags[o] = (uint8_t)fl;
+        if (A.rec_reward != nullptr) {                  // joints-only records: reward / flags go to the event sink
+            __stcs(A.rec_reward + o, rw);
+            A.rec_flags[o] = (uint8_t)fl;
+        }
     }
 }
 
@@ -157,7 +175,7 @@ __device__ __forceinline__ void store_uneventful(const RolloutDev &A, int64_t o,
     if (RECORD) {
         __stcs(A.rec_j1 + o, (float)q1);
         __stcs(A.rec_j2 + o, (float)q2);
-        if (!A.zfill) {
+        if (!A.zfill && A.rec_reward != nullptr) {
             __stcs(A.rec_reward + o, 0.0f);
             A.rec_flags[o] = 0;
         }
@@ -167,6 +185,7 @@ __device__ __forceinline__ void store_uneventful(const RolloutDev &A, int64_t o,
 // warp-cooperative zero fill of rows [0, K) x this warp's 32 envs of the reward (128 B per row) and flags (32 B per
 // row) planes.  warp_e0: first env of the warp (a multiple of 32).
 __device__ __forceinline__ void zero_fill_warp(const RolloutDev &A, int64_t warp_e0) {
+    if (A.rec_reward == nullptr) return;                // joints-only records
     const int lane = threadIdx.x & 31;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = lane >> 3; t < A.K; t += 4)            // 8 lanes x 16 B = one 128-byte row segment; 4 rows per store

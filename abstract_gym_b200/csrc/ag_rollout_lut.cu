@@ -173,11 +173,12 @@ __device__ __forceinline__ void settle_step(const ag_params &P, const GridDev &G
     if (d & 1) { rw = (float)P.reward_collision; f |= AG_FLAG_COLLISION; }       // scene_0.py:95-97
     if (d & 2) { rw = (float)P.reward_reach; f |= AG_FLAG_DONE; }                // :98-100
     if (d >> 2) add64(s_acc, AG_ST_AXIS_ALIGNED, d >> 2);
-    if (RECORD && (f != 0 || rw != 0.0f)) {                                      // experiment_0.py:23-25 (joints already stored)
+    if (RECORD && A.rec_reward != nullptr && (f != 0 || rw != 0.0f)) {           // experiment_0.py:23-25 (joints already stored)
         const int64_t o = (int64_t)t * A.row_stride + e;
         __stcs(A.rec_reward + o, rw);
         A.rec_flags[o] = (uint8_t)f;
     }
+    emit_event(A, e, t, rw, f);
     if (f) {                                                                     // experiment_0.py:30-34
         cold = true;
         add64(s_acc, AG_ST_EPISODES, 1);

@@ -103,12 +103,15 @@ class DeviceGrid:
         return cls(bits, S, environment_size, n_grids=G, envs_per_grid=envs_per_grid, bits_t=bits_t,
                    max_occupied=int(occ8.sum(dim=(1, 2), dtype=torch.int64).max().item()))
 
-    def unpack(self):
-        """[G,S,S] uint8 numpy (inverse of the packing; for tests and tools)"""
-        w = self.bits.cpu().numpy().view(np.uint32).reshape(self.n_grids, self.stride_words)
-        w = w[:, :self.S * self.words_per_row].reshape(self.n_grids, self.S, self.words_per_row)
+    def unpack(self, indices=None):
+        """[G,S,S] uint8 numpy (inverse of the packing; for tests and tools); `indices`: only these grids"""
+        bits = self.bits.view(self.n_grids, self.stride_words)
+        if indices is not None:
+            bits = bits[torch.as_tensor(list(indices), device=self.device, dtype=torch.long)]
+        w = bits.cpu().numpy().view(np.uint32).reshape(-1, self.stride_words)
+        w = w[:, :self.S * self.words_per_row].reshape(-1, self.S, self.words_per_row)
         b = ((w[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(np.uint8)
-        return b.reshape(self.n_grids, self.S, self.words_per_row * 32)[:, :, :self.S]
+        return b.reshape(w.shape[0], self.S, self.words_per_row * 32)[:, :, :self.S]
 
 
 class OccupancyGrid:

@@ -204,7 +204,7 @@ class BatchedScene:
         self._reset(mask, reset_u, False)
 
     # ---- K4 ------------------------------------------------------------------------------------
-    def _rollout_args(self, K, actions, reset_u, rec, engine, targets=None, diag=True):
+    def _rollout_args(self, K, actions, reset_u, rec, engine, targets=None, diag=True, events=None):
         a = _lib.RolloutArgs()
         a.n, a.env_id0, a.K = self.n, self.env_id0, int(K)
         a.engine = self.engine if engine is None else _engine(engine)
@@ -219,7 +219,10 @@ class BatchedScene:
         if rec is not None:
             a.rec_j1, a.rec_j2 = rec["j1"].data_ptr(), rec["j2"].data_ptr()
             a.rec_reward = rec["reward"].data_ptr() if rec.get("reward") is not None else None
-            a.rec_flags = rec["flags"].data_ptr()
+            a.rec_flags = rec["flags"].data_ptr() if rec.get("flags") is not None else None
+        if events is not None:
+            a.events, a.event_count = events["events"].data_ptr(), events["count_buf"].data_ptr()
+            a.event_capacity = events["events"].shape[0]
         a.stats = self.stats.data_ptr()
         a.diag = self.diag.data_ptr() if diag else None
         a.targets = None if targets is None else targets.data_ptr()
@@ -246,7 +249,8 @@ class BatchedScene:
         out[(f & _lib.FLAG_DONE) != 0] = float(p.reward_reach)
         return out
 
-    def rollout(self, K, actions=None, reset_u=None, record=True, out=None, engine=None, targets=None, diag=True):
+    def rollout(self, K, actions=None, reset_u=None, record=True, out=None, engine=None, targets=None, diag=True,
+                events=None):
         """The loop body of experiment/experiment_0.py:20-34, K times, in ONE kernel:
         action -> step -> record -> reset when done or collision.
 
@@ -259,6 +263,8 @@ class BatchedScene:
         targets: optional [N,2] float64 per-env cartesian targets replacing target_c in the reach test
                  (scene_0.py:129-130); ignored in joint-target mode.
         diag   : accumulate the FAST-filter diagnostics into self.diag (a few shared-memory atomics per warp exit).
+        events : optional event sink from alloc_event_sink(device tensors): every eventful step appends
+                 (env, step << 8 | flags, reward bits); with it `out` may hold the joint planes only.
         """
         if actions is not None:
             actions = torch.as_tensor(actions, device=self.device)
@@ -272,10 +278,73 @@ class BatchedScene:
             rec = out if out is not None else self.alloc_records(K)
         if targets is not None:
             targets = as_f64(targets, self.device).reshape(self.n, 2).contiguous()
-        a = self._rollout_args(K, actions, reset_u, rec, engine, targets, diag)
+        a = self._rollout_args(K, actions, reset_u, rec, engine, targets, diag, events)
         g = self.grid.c_struct()
         _lib.check(self._lib.ag_rollout(self.params(), g, C.byref(a), stream_ptr(self.device)), "ag_rollout")
         return rec
+
+    # ---- event-compacted sink: joints per step, reward / flags only where something happened ----
+    def alloc_event_sink(self, K, capacity=None, pinned_host=False):
+        """Buffers of the compact trajectory form: the two joint planes [K,N] float32 and an event list
+        [capacity,3] uint32 = (env, step << 8 | flags, float32 bits of step_reward) for the eventful env-steps (terminal
+        steps: ~0.1 % on scene_0).  `count_buf` is the int64 event counter the kernels advance (reset it between device
+        rollouts); `count` holds the number of events of the last rollout_events_host call."""
+        kw = dict(device="cpu", pin_memory=True) if pinned_host else dict(device=self.device)
+        cap = int(capacity) if capacity is not None else max(1024, (K * self.n) // 16)
+        return dict(j1=torch.empty(K, self.n, dtype=torch.float32, **kw), j2=torch.empty(K, self.n, dtype=torch.float32, **kw),
+                    events=torch.zeros(cap, 3, dtype=torch.int32, **kw), count_buf=torch.zeros(1, dtype=torch.int64, **kw), count=0)
+
+    @staticmethod
+    def decode_events(sink, count=None):
+        """(env [M], step [M], flags [M], reward [M]) numpy arrays of the first `count` events of a sink (host side)."""
+        c = int(sink["count"] if count is None else count)
+        c = min(c, sink["events"].shape[0])
+        ev = sink["events"][:c].cpu().numpy().view(np.uint32)
+        return (ev[:, 0].astype(np.int64), (ev[:, 1] >> 8).astype(np.int64), (ev[:, 1] & 0xFF).astype(np.uint8),
+                ev[:, 2].copy().view(np.float32))
+
+    def events_to_planes(self, sink, K, count=None):
+        """Rebuild the dense reward / flags planes [K,N] of a rollout from its event list (numpy)."""
+        env, step, fl, rw = self.decode_events(sink, count)
+        reward = np.zeros((K, self.n), dtype=np.float32)
+        flags = np.zeros((K, self.n), dtype=np.uint8)
+        reward[step, env] = rw
+        flags[step, env] = fl
+        return reward, flags
+
+    def rollout_events_host(self, K, sink, chunk_steps=4, engine=None):
+        """End-to-end form with the least bytes on the bus: the actions are drawn in the kernel (Philox stream 0 keyed by
+        (seed, global env id, step counter) -- `philox_actions` reproduces any env's actions on the host), nothing goes
+        host -> device; the joint planes stream out (8 B per env-step) and reward / flags only as events (12 B each).
+        `sink` = alloc_event_sink(K, pinned_host=True).  Returns the episode statistics of this call."""
+        cap = sink["events"].shape[0]
+        key = ("events", K, int(chunk_steps), cap)
+        if key not in self._pipelines:
+            h = C.c_void_p()
+            _lib.check(self._lib.ag_pipeline_create(C.byref(h), self.device.index, self.n, K, 1 << 17, max(1, int(chunk_steps)),
+                                                    1, cap), "ag_pipeline_create")
+            self._pipelines[key] = h
+        a = self._rollout_args(K, None, None, dict(j1=sink["j1"], j2=sink["j2"]), engine, None, False, sink)
+        a.stats = None
+        g = self.grid.c_struct()
+        st = np.zeros(_lib.ST_COUNT, dtype=np.int64)
+        torch.cuda.current_stream(self.device).synchronize()   # env state must be settled
+        _lib.check(self._lib.ag_rollout_host(self._pipelines[key], self.params(), g, C.byref(a),
+                                             st.ctypes.data_as(C.c_void_p)), "ag_rollout_host")
+        sink["count"] = int(sink["count_buf"][0].item())
+        self.stats += torch.from_numpy(st).to(self.device)
+        return dict(zip(_lib.STAT_NAMES, st.tolist()))
+
+    def philox_actions(self, env_ids, step_ctr0, K):
+        """The float64 actions the kernels draw for local envs `env_ids` at draw indices step_ctr0 .. step_ctr0+K-1
+        (scene_0.py:84-85 with Philox4x32-10 stream 0 keyed by (seed, global env id)): [K, len(env_ids), 2]."""
+        from ..utils.philox import uniform2
+        env_ids = np.asarray(env_ids, dtype=np.uint64)
+        gid = env_ids + np.uint64(self.env_id0)
+        draws = (np.asarray(step_ctr0, dtype=np.uint64).reshape(1, -1) + np.arange(K, dtype=np.uint64).reshape(-1, 1))
+        u0, u1 = uniform2(self.seed, np.broadcast_to(gid, draws.shape), draws, 0)
+        scale = float(self.params().action_scale)
+        return np.stack([(u0 - 0.5) * scale, (u1 - 0.5) * scale], axis=-1)
 
     def rollout_host(self, K, actions_host=None, out_host=None, chunk_envs=1 << 17, engine=None, chunk_steps=0):
         """End-to-end form of `rollout` for host-resident data: actions_host [K,N,2] float32 and
@@ -288,7 +357,7 @@ class BatchedScene:
         if key not in self._pipelines:
             h = C.c_void_p()
             _lib.check(self._lib.ag_pipeline_create(C.byref(h), self.device.index, self.n, K, int(chunk_envs),
-                                                    int(chunk_steps), 1 if record else 0), "ag_pipeline_create")
+                                                    int(chunk_steps), 1 if record else 0, 0), "ag_pipeline_create")
             self._pipelines[key] = h
         if actions_host is not None:
             if actions_host.dtype != torch.float32 or tuple(actions_host.shape) != (K, self.n, 2) \

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AG_ABI_VERSION 3
+#define AG_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define AG_API __attribute__((visibility("default")))
@@ -189,7 +189,8 @@ AG_API ag_status ag_reset(const ag_params *p, const ag_grid *g, double *j1, doub
 /* K4: the rollout loop experiment/experiment_0.py:20-34 fused over K steps:
  *   action -> step -> record -> if done|collision: reset.
  * actions: [K][n][2] float32, or NULL = Philox stream 0 (float64 (u-0.5)*action_scale).
- * reset_u: as ag_reset.  rec_*: [K][n] or all NULL (statistics only).
+ * reset_u: as ag_reset.  rec_*: [K][n]; all four, or rec_j1 + rec_j2 only (with or without the event sink), or all
+ * NULL (statistics only).
  * stats: int64[AG_ST_COUNT], accumulated with one atomic per block per slot. */
 typedef struct ag_rollout_args {
     int64_t n;
@@ -211,6 +212,17 @@ typedef struct ag_rollout_args {
     int64_t *diag;           /* optional int64[AG_DIAG_COUNT] filter diagnostics (accumulated), or NULL */
     const double *targets;   /* optional [n][2] float64 per-env cartesian targets replacing Scene.target_c in the reach
                               * test (scenario/scene_0.py:129-130), or NULL = p->target_x/y; ignored in joint-target mode */
+    /* Event sink (optional).  In a rollout record reward and flags are zero for all but the terminal steps (~0.1 % of
+     * the env-steps on scene_0), so a caller may leave rec_reward / rec_flags NULL (rec_j1 / rec_j2 only) and collect
+     * the eventful steps here instead: events[3*i] = local env index, events[3*i+1] = (step << 8) | flags with
+     * step = event_step0 + step within this launch, events[3*i+2] = the float32 bits of step_reward.  *event_count is
+     * advanced by one per event (atomically, in no particular order); events beyond event_capacity are counted but
+     * not stored. */
+    uint32_t *events;
+    int64_t *event_count;
+    int64_t event_capacity;
+    int32_t event_step0;
+    int32_t reserved2;
 } ag_rollout_args;
 
 AG_API ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream);
@@ -228,13 +240,18 @@ typedef struct ag_pipeline ag_pipeline;
  * sliced over steps (all envs, chunk_steps steps per stage; contiguous copies -- the faster form); otherwise over
  * envs (chunk_envs envs per stage, all K steps: one kernel launch per env slice). */
 AG_API ag_status ag_pipeline_create(ag_pipeline **out, int32_t device, int64_t n, int32_t K,
-                             int64_t chunk_envs, int32_t chunk_steps, int32_t record);
+                             int64_t chunk_envs, int32_t chunk_steps, int32_t record, int64_t event_capacity);
 AG_API void ag_pipeline_destroy(ag_pipeline *pl);
 /* Same as ag_rollout but actions / rec_* / stats_host are HOST pointers (pinned for full speed);
  * env state pointers inside `a` stay DEVICE pointers (the state lives in HBM between calls).
  * a->rec_reward may be NULL while the other three record pointers are set ("compact records": the reward of a
  * rollout record is a function of its flags -- reward_reach if done, else reward_collision if collision, else 0 --
- * so it need not cross PCIe).  Returns after all records and stats are on the host. */
+ * so it need not cross PCIe).  a->actions == NULL: the actions are drawn in the kernel (Philox stream 0), nothing is
+ * copied to the device.  a->events / a->event_count: HOST pointers here (the pipeline was created with
+ * event_capacity > 0); the events of the whole call are appended from index 0, *event_count is SET to their number.
+ * stats_host (int64[AG_ST_COUNT], may be NULL) is ACCUMULATED into: zero it to get this call's counters.
+ * Returns after all records, events and stats are on the host; on failure every stream of the pipeline has been
+ * synchronised, so no copy is still writing the caller's buffers.  The caller's current device is preserved. */
 AG_API ag_status ag_rollout_host(ag_pipeline *pl, const ag_params *p, const ag_grid *g,
                           const ag_rollout_args *a, int64_t *stats_host);
 

@@ -17,11 +17,15 @@ import sys
 import tempfile
 import types
 
-REFERENCE_ROOT = os.environ.get("ABSTRACT_GYM_REFERENCE", "/root/reference")
+def _root() -> str:
+    return os.environ.get("ABSTRACT_GYM_REFERENCE", "/root/reference")
+
+
+REFERENCE_ROOT = _root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "scenario", "scene_0.py"))
+    return os.path.isfile(os.path.join(_root(), "scenario", "scene_0.py"))
 
 
 def _stub_matplotlib():
@@ -59,10 +63,10 @@ def boot():
     if _booted is not None:
         return _booted
     if not available():
-        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+        raise RuntimeError("reference tree not found at %s" % _root())
     _stub_matplotlib()
     parent = tempfile.mkdtemp(prefix="ag_ref_")
-    os.symlink(REFERENCE_ROOT, os.path.join(parent, "abstract_gym"))
+    os.symlink(_root(), os.path.join(parent, "abstract_gym"))
     sys.path.insert(0, parent)
     sys.path.insert(0, os.path.join(parent, "abstract_gym"))  # makes ``import __init__`` resolve
     sys.dont_write_bytecode = True  # /root/reference is read-only

@@ -860,3 +860,203 @@ def test_rollout_random_grids_sweep(ag, torch_, oracle):
             _rollout_case(ag, torch_, oracle, [random_grid(rng, S, p)], n, K, "fast", bool(i % 2), seed=100 + i)
         cases += 1
     assert cases == 24
+
+
+# ------------------------------------------------------------------ round 2: config-size parity, sinks, filters
+
+def _sampled_fullsize(ag, torch, oracle, scene, grid_squares_of_chunk, n, K, chunk, n_chunks, seed, epg=None):
+    """Launch the whole batch (in-kernel Philox actions and resets), then re-run `n_chunks` random contiguous chunks of
+    `chunk` global env ids on the oracle: Philox is keyed by the global id, so every recorded flag / reward / joint of
+    the sampled envs, their final state and counters must match bit for bit."""
+    j1_0, j2_0 = scene.robot.joint_1.cpu().numpy().copy(), scene.robot.joint_2.cpu().numpy().copy()
+    rc0 = scene.reset_ctr.cpu().numpy().view(np.uint32).copy()
+    rec = scene.rollout(K, actions=None, record=True)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(seed)
+    starts = rng.choice(n // chunk, size=n_chunks, replace=False) * chunk
+    fl, rw = rec["flags"].cpu().numpy(), rec["reward"].cpu().numpy()
+    r1, r2 = rec["j1"].cpu().numpy(), rec["j2"].cpu().numpy()
+    fin1, fin2 = scene.robot.joint_1.cpu().numpy(), scene.robot.joint_2.cpu().numpy()
+    rcn = scene.reset_ctr.cpu().numpy().view(np.uint32)
+    eln = scene.ep_len.cpu().numpy().view(np.uint32)
+    episodes = 0
+    for s0 in starts:
+        sl = slice(int(s0), int(s0) + chunk)
+        st = oracle.RolloutState(j1_0[sl], j2_0[sl])
+        st.reset_ctr[:] = rc0[sl]
+        orec, ostats = oracle.rollout(st, K, [grid_squares_of_chunk(int(s0))], envs_per_grid=None, env_id0=scene.env_id0 + int(s0),
+                                      seed=scene.seed)
+        assert np.array_equal(fl[:, sl], orec["flags"]), "flags differ in chunk %d" % s0
+        assert np.array_equal(rw[:, sl], orec["reward"])
+        assert np.array_equal(r1[:, sl], orec["j1"]) and np.array_equal(r2[:, sl], orec["j2"])
+        assert np.array_equal(fin1[sl], st.j1) and np.array_equal(fin2[sl], st.j2)
+        assert np.array_equal(rcn[sl], st.reset_ctr) and np.array_equal(eln[sl], st.ep_len)
+        episodes += int(ostats[oracle.ST_EPISODES])
+    return episodes
+
+
+@pytest.mark.gpu
+def test_fullsize_config4_sampled_vs_oracle(ag, torch_, oracle):
+    """BASELINE config 4 at its full size (2^20 envs x 64 steps on the bench's 1024x1024 Bernoulli(0.002) map, FAST
+    engine, lane-asynchronous kernel): 16 x 256 = 4096 sampled global env ids against the oracle, all 64 steps."""
+    n, K = 1 << 20, 64
+    occ = (np.random.default_rng(4).random((1024, 1024)) < 0.002).astype(np.uint8)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    g.load_from_matrix(occ)
+    gen = torch_.Generator(device="cuda").manual_seed(1234)
+    sc = ag.BatchedScene(ag.BatchedTwoJointRobot.random(n, device="cuda", generator=gen), g, engine="fast", seed=0)
+    sc.random_valid_pose()
+    sq = oracle.grid_squares(occ)[0]
+    episodes = _sampled_fullsize(ag, torch_, oracle, sc, lambda s0: sq, n, K, 256, 16, seed=44)
+    assert episodes > 50000                                  # ~57 % of the env-steps end an episode on this map
+    assert sc.stats_dict()["env_steps"] == n * K
+
+
+@pytest.mark.gpu
+def test_fullsize_config5_sampled_vs_oracle(ag, torch_, oracle):
+    """BASELINE config 5 at its full size: 4096 distinct 256x256 Bernoulli(0.008) maps (bench generator), 2^20 envs x
+    64 steps, auto-reset; 16 sampled batches of 256 envs (each on its own map) against the oracle."""
+    n, K = 1 << 20, 64
+    ggen = torch_.Generator(device="cuda").manual_seed(5)
+    grid = ag.BatchedOccupancyGrid.random(n // 256, 256, 0.008, 256, device="cuda", generator=ggen, clear_base_cells=2)
+    gen = torch_.Generator(device="cuda").manual_seed(1234)
+    sc = ag.BatchedScene(ag.BatchedTwoJointRobot.random(n, device="cuda", generator=gen), grid, engine="fast", seed=0)
+    sc.random_valid_pose()
+    dg = grid.device_grid()
+
+    def squares(s0):
+        occ = dg.unpack([s0 // 256])[0]
+        assert occ[126:131, 125:130].sum() == 0              # the cells around the base are free
+        return oracle.grid_squares(occ)[0]
+
+    episodes = _sampled_fullsize(ag, torch_, oracle, sc, squares, n, K, 256, 16, seed=55)
+    assert episodes > 20000 and sc.stats_dict()["stuck_resets"] == 0
+
+
+@pytest.mark.gpu
+def test_dense_pooled_kernel_equals_default(ag, torch_, oracle):
+    """the opt-in warp-cooperative kernel for dense maps (csrc/ag_dense.cu, AG_DENSE_POOLED=1) against the oracle, in a
+    child process (the switch is read once per process)"""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+import abstract_gym_b200 as ag
+from oracle import oracle as orc
+rng = np.random.default_rng(5)
+occs = [(rng.random((256, 256)) < 0.008).astype(np.uint8) for _ in range(4)]
+n, K = 1024, 12
+j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+g = ag.BatchedOccupancyGrid(torch.as_tensor(np.stack(occs), device="cuda"), 256)
+sc = ag.BatchedScene(ag.BatchedTwoJointRobot(torch.as_tensor(j1, device="cuda"), torch.as_tensor(j2, device="cuda")), g, engine="fast", seed=3)
+rec = sc.rollout(K)
+torch.cuda.synchronize()
+st = orc.RolloutState(j1, j2)
+orec, ostats = orc.rollout(st, K, [orc.grid_squares(o)[0] for o in occs], envs_per_grid=256, seed=3)
+assert np.array_equal(rec["flags"].cpu().numpy(), orec["flags"]) and np.array_equal(rec["j1"].cpu().numpy(), orec["j1"])
+assert np.array_equal(sc.stats.cpu().numpy(), ostats) and np.array_equal(sc.robot.joint_1.cpu().numpy(), st.j1)
+print("pooled ok", int(ostats[0]))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AG_DENSE_POOLED="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "pooled ok" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid_kind", ["scene0", "rand64"])
+def test_event_sink_equals_dense_records(ag, torch_, grid_kind):
+    """joints-only records + the event list (ag_rollout_args.events) carry exactly what the four dense planes carry"""
+    n, K = 8192, 48
+    rng = np.random.default_rng(71)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    if grid_kind == "rand64":
+        g.load_from_matrix(random_grid(rng, 64, 0.01))
+    a = make_scene(ag, torch_, g, j1, j2, engine="fast", seed=5)
+    b = make_scene(ag, torch_, g, j1, j2, engine="fast", seed=5)
+    dense = a.rollout(K)
+    sink = b.alloc_event_sink(K)
+    b.rollout(K, out=dict(j1=sink["j1"], j2=sink["j2"]), events=sink)
+    torch_.cuda.synchronize()
+    cnt = int(sink["count_buf"][0].item())
+    assert 0 < cnt <= sink["events"].shape[0]
+    reward, flags = b.events_to_planes(sink, K, count=cnt)
+    assert np.array_equal(flags, dense["flags"].cpu().numpy()) and np.array_equal(reward, dense["reward"].cpu().numpy())
+    assert np.array_equal(sink["j1"].cpu().numpy(), dense["j1"].cpu().numpy())
+    assert cnt == int((dense["flags"].cpu().numpy() != 0).sum())
+    assert np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_rollout_events_host_and_philox_actions(ag, torch_):
+    """the zero-H2D host path: in-kernel actions, joints + events to pinned host memory, equal to the device rollout;
+    philox_actions() reproduces on the host the actions an env drew in the kernel"""
+    n, K = 1 << 14, 32
+    rng = np.random.default_rng(72)
+    j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    a = make_scene(ag, torch_, g, j1, j2, engine="fast", seed=9)
+    b = make_scene(ag, torch_, g, j1, j2, engine="fast", seed=9)
+    a.random_valid_pose(); b.random_valid_pose()
+    start1, start2 = a.robot.joint_1.cpu().numpy().copy(), a.robot.joint_2.cpu().numpy().copy()
+    for call in range(2):                                     # two calls: the draw counters carry over
+        dense = a.rollout(K)
+        sink = b.alloc_event_sink(K, pinned_host=True)
+        st = b.rollout_events_host(K, sink, chunk_steps=5)
+        torch_.cuda.synchronize()
+        reward, flags = b.events_to_planes(sink, K)
+        assert np.array_equal(flags, dense["flags"].cpu().numpy()) and np.array_equal(reward, dense["reward"].cpu().numpy())
+        assert np.array_equal(sink["j1"].numpy(), dense["j1"].cpu().numpy()) and np.array_equal(sink["j2"].numpy(), dense["j2"].cpu().numpy())
+        assert st["env_steps"] == n * K
+        if call == 0:
+            quiet = np.flatnonzero((flags != 0).sum(axis=0) == 0)[:512]     # envs without an episode end
+            acts = b.philox_actions(quiet, np.zeros(len(quiet), dtype=np.uint64), K)   # [K, m, 2] float64
+            q1, q2 = start1[quiet].copy(), start2[quiet].copy()
+            for t in range(K):
+                q1 = q1 + acts[t, :, 0]; q2 = q2 + acts[t, :, 1]
+                assert np.array_equal(q1.astype(np.float32), sink["j1"].numpy()[t, quiet])
+                assert np.array_equal(q2.astype(np.float32), sink["j2"].numpy()[t, quiet])
+    assert np.array_equal(a.robot.joint_1.cpu().numpy(), b.robot.joint_1.cpu().numpy())
+    assert np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_fast_filter_band_1e3_to_2p20_rad(ag, torch_, oracle):
+    """FAST == EXACT == oracle for joint angles between 1e3 and 2^20 rad, the range where the float32 filter trusts its
+    float64 range reduction most (beyond 2^20 it hands over to float64): same poses, many whole turns away."""
+    n = 1 << 18
+    rng = np.random.default_rng(81)
+    base1, base2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    turns = np.round(10.0 ** rng.uniform(np.log10(1.6e2), np.log10(1.66e5), n)) * rng.choice([-1.0, 1.0], n)   # 1e3 .. 1.04e6 rad
+    j1, j2 = base1 + 2 * np.pi * turns, base2 + 2 * np.pi * np.roll(turns, 1)
+    assert np.abs(j1).max() < 2 ** 20 and np.abs(j1).min() > 9e2
+    g = ag.OccupancyGrid(size=9, random_obstacle=False)
+    sq, ci = oracle.manual_grid()
+    ref = oracle.collision_batch(j1, j2, sq, want_first_hit=False)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    for engine in ("fast", "exact"):
+        sc = make_scene(ag, torch_, g, j1, j2, engine=engine)
+        hit = sc.collision_check().cpu().numpy()
+        bad = np.flatnonzero(hit != (ref != 0))
+        assert len(bad) == 0, "%s: %d flags differ" % (engine, len(bad))
+    # and through the fused rollout (table arm of k_rollout_lut): a short rollout from these poses
+    K = 8
+    acts = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32)
+    sc = make_scene(ag, torch_, g, j1, j2, engine="fast", seed=4)
+    sc.random_valid_pose()
+    st = oracle.RolloutState(sc.robot.joint_1.cpu().numpy(), sc.robot.joint_2.cpu().numpy())
+    st.reset_ctr[:] = sc.reset_ctr.cpu().numpy().view(np.uint32)
+    _compare_rollout(ag, torch_, oracle, sc, st, K, acts, oracle.default_params(), [sq])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,p", [(320, 0.004), (440, 0.003)])
+def test_exact_rollout_with_large_staged_grids(ag, torch_, oracle, S, p):
+    """EXACT / BRUTE rollouts on grids whose staging footprint plus the kernel's static shared memory exceeds 48 KB
+    (S = 320 with the transposed copy: 30.7 KB dynamic + 22.6 KB static): needs the dynamic shared-memory opt-in."""
+    rng = np.random.default_rng(S)
+    occ = random_grid(rng, S, p)
+    occ[S // 2 - 3:S // 2 + 4, S // 2 - 3:S // 2 + 4] = 0
+    for engine in ("exact", "fast"):
+        _rollout_case(ag, torch_, oracle, [occ], 768, 6, engine, True, seed=8)
