@@ -80,6 +80,8 @@ SYMBOLS = {
                        _i64, _i64, _i32, _vp]),
     "ag_reset": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _u64, _i32,
                         _vp, _i64, _i64, _i32, _vp]),
+    "ag_step_obs": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                           _vp, _vp, _i32, _vp, _u64, _i32, _i64, _i64, _i32, _vp]),
     "ag_rollout": (_i32, [C.POINTER(Params), C.POINTER(Grid), C.POINTER(RolloutArgs), _vp]),
     "ag_launch_count": (_i64, []),
     "ag_pipeline_create": (_i32, [C.POINTER(_vp), _i32, _i64, _i32, _i64, _i32, _i32, _i64]),

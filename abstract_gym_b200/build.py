@@ -17,6 +17,10 @@ LIB = os.environ.get("AG_LIB_PATH") or os.path.join(HERE, "libabstract_gym_b200.
 SOURCES = ["ag_kernels.cu", "ag_rollout_lut.cu", "ag_dense.cu", "ag_host.cu"]
 HEADERS = ["ag_device.cuh", "ag_fast.cuh", "ag_rollout.cuh", os.path.join(INCLUDE, "abstract_gym_b200.h")]
 OBJDIR = os.path.join(HERE, "build")
+# the compiled torch custom-op library (torch.ops.abstract_gym_b200.*): a C++ shim over the C ABI, linked against
+# libabstract_gym_b200.so (rpath $ORIGIN) and the torch libraries of the running interpreter
+OPS_LIB = os.path.join(HERE, "libabstract_gym_b200_ops.so")
+OPS_SRC = os.path.join(CSRC, "ag_torch_ops.cpp")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -85,6 +89,46 @@ def build(force: bool = False, verbose: bool = False, out: str = None) -> str:
     return target
 
 
+def ops_needs_build() -> bool:
+    if not os.path.exists(OPS_LIB):
+        return True
+    t = os.path.getmtime(OPS_LIB)
+    deps = [OPS_SRC, os.path.join(INCLUDE, "abstract_gym_b200.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_ops(force: bool = False, verbose: bool = False) -> str:
+    """g++ -shared csrc/ag_torch_ops.cpp -> libabstract_gym_b200_ops.so (needs libabstract_gym_b200.so: build() first)"""
+    if not force and not ops_needs_build():
+        return OPS_LIB
+    build()
+    import torch
+    from torch.utils import cpp_extension as ce
+    cxx = shutil.which("g++") or "g++"
+    abi = int(getattr(torch._C, "_GLIBCXX_USE_CXX11_ABI", 1))
+    cuda_home = os.environ.get("CUDA_HOME") or "/usr/local/cuda"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-D_GLIBCXX_USE_CXX11_ABI=%d" % abi,
+           "-DTORCH_API_INCLUDE_EXTENSION_H"]
+    for inc in ce.include_paths() + [os.path.join(cuda_home, "include"), INCLUDE]:
+        cmd += ["-I", inc]
+    cmd += [OPS_SRC, "-o", OPS_LIB]
+    for d in ce.library_paths():
+        cmd += ["-L", d]
+    cmd += ["-L", HERE, "-L", os.path.join(cuda_home, "lib64"), "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+            "-labstract_gym_b200", "-lcudart", "-Wl,-rpath,$ORIGIN"]
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(os.path.join(HERE, "build_ops.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed (%d) building the torch op library; see build_ops.log" % r.returncode)
+    return OPS_LIB
+
+
 if __name__ == "__main__":
     out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out))
+    if out is None:
+        print(build_ops(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

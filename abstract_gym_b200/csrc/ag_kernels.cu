@@ -217,6 +217,92 @@ __global__ void __launch_bounds__(AG_BLOCK) k_reset(const ag_params P, const Gri
     stats_flush(s_acc, stats);
 }
 
+// ------------------------------------------------------------------------------------------- K6
+// The gym-style step of scenario/vector_env.py in ONE launch: Scene.step (scene_0.py:88-103), the terminal
+// observation, the episode statistics and Scene.reset() of experiment_0.py:30-34 (same-step auto-reset), and the
+// observation of the pose the env continues from.  obs / final_obs: [n][AG_OBS_DIM] float64 =
+// (joint_1, joint_2, EE_x, EE_y, |target_x - EE_x|, |target_y - EE_y|); crop: optional [n][c][c] uint8 occupancy of
+// the c x c cells centred on the end effector's cell (1 = occupied, 2 = outside the grid), row 0 = top.
+__device__ __forceinline__ void write_obs(double *o, double q1, double q2, const Arm &A, double tx, double ty) {
+    reinterpret_cast<double2 *>(o)[0] = make_double2(q1, q2);
+    reinterpret_cast<double2 *>(o)[1] = make_double2(A.gx, A.gy);
+    reinterpret_cast<double2 *>(o)[2] = make_double2(fabs(__dsub_rn(tx, A.gx)), fabs(__dsub_rn(ty, A.gy)));
+}
+
+template <int ENGINE, bool ACT_F32>
+__global__ void __launch_bounds__(AG_BLOCK) k_step_obs(const ag_params P, const GridDev G, double *__restrict__ j1,
+                                                       double *__restrict__ j2, const void *__restrict__ actions,
+                                                       float *__restrict__ reward, uint8_t *__restrict__ flags,
+                                                       uint32_t *__restrict__ reset_ctr, uint32_t *__restrict__ ep_len,
+                                                       const double *__restrict__ targets, double *__restrict__ obs,
+                                                       float *__restrict__ reward_out, uint8_t *__restrict__ terminated,
+                                                       uint8_t *__restrict__ collision, double *__restrict__ final_obs,
+                                                       uint8_t *__restrict__ crop, int crop_size, unsigned long long *stats,
+                                                       uint64_t seed, int auto_reset, int64_t n, int64_t env_id0) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ FastList s_fl;
+    __shared__ unsigned long long s_acc[AG_ST_COUNT];
+    if (threadIdx.x < AG_ST_COUNT) s_acc[threadIdx.x] = 0;
+    const BlockCtx B = block_prologue<ENGINE>(G, env_id0, n, smem, &s_fl);
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+        const FastConst C = make_fast_const(P, G);
+        double tx = P.target_x, ty = P.target_y;
+        if (targets) { const double2 tg = reinterpret_cast<const double2 *>(targets)[e]; tx = tg.x; ty = tg.y; }
+        double d1, d2;
+        if (ACT_F32) { const float2 a = reinterpret_cast<const float2 *>(actions)[e]; d1 = (double)a.x; d2 = (double)a.y; }
+        else { const double2 a = reinterpret_cast<const double2 *>(actions)[e]; d1 = a.x; d2 = a.y; }
+        double q1 = __dadd_rn(j1[e], d1), q2 = __dadd_rn(j2[e], d2);          // two_joint_robot.py:71-72
+        float rw = reward[e];
+        uint32_t fl = flags[e];
+        Arm A = forward_kinematics(q1, q2, P.link_1, P.link_2);
+        int fh = INT_MAX, axis = 0;
+        bool h;
+        if constexpr (ENGINE == AG_ENGINE_FAST) h = fast_arm_collides(P, G, B.V, B.fl, C, A, axis);
+        else h = arm_collides<ENGINE, false>(G, B.V, A, P.section_eps, fh, axis);
+        if (h) { rw = (float)P.reward_collision; fl |= AG_FLAG_COLLISION; }      // scene_0.py:95-97
+        const bool reached = P.choose_j_tar ? target_reached_joint(P, q1, q2)
+                                            : (fabs(__dsub_rn(tx, A.gx)) < P.reach_eps && fabs(__dsub_rn(ty, A.gy)) < P.reach_eps);
+        if (reached) { rw = (float)P.reward_reach; fl |= AG_FLAG_DONE; }         // :98-100
+        reward_out[e] = rw;
+        terminated[e] = fl != 0 ? 1 : 0;
+        collision[e] = (fl & AG_FLAG_COLLISION) ? 1 : 0;
+        if (final_obs) write_obs(final_obs + e * AG_OBS_DIM, q1, q2, A, tx, ty);
+        uint32_t el = ep_len[e] + 1;
+        acc32(s_acc, AG_ST_ENV_STEPS, 1);
+        if (fl != 0 && auto_reset) {                                             // experiment_0.py:30-34
+            acc32(s_acc, AG_ST_EPISODES, 1);
+            if (fl & AG_FLAG_COLLISION) acc32(s_acc, AG_ST_COLLISIONS, 1);
+            if (fl & AG_FLAG_DONE) acc32(s_acc, AG_ST_SUCCESSES, 1);
+            atomicAdd(&s_acc[AG_ST_EP_LEN_SUM], (unsigned long long)el);
+            acc32(s_acc, AG_ST_RETURN_MILLI, __float2int_rn(rw * 1e-3f));
+            if (h) {                                                             // Scene.reset(): resample only while colliding
+                uint32_t rc = reset_ctr[e];
+                resample_pose<ENGINE, false>(P, G, B, C, true, q1, q2, rc, nullptr, 0, seed, (uint64_t)(env_id0 + e), s_acc);
+                reset_ctr[e] = rc;
+                A = forward_kinematics(q1, q2, P.link_1, P.link_2);
+            }
+            rw = 0.0f; fl = 0; el = 0;                                           // scene_0.py:111-113
+        }
+        if (axis) acc32(s_acc, AG_ST_AXIS_ALIGNED, axis);
+        j1[e] = q1; j2[e] = q2; reward[e] = rw; flags[e] = (uint8_t)fl; ep_len[e] = el;
+        write_obs(obs + e * AG_OBS_DIM, q1, q2, A, tx, ty);
+        if (crop) {                                                              // local occupancy around the end effector
+            const int r0 = row_of(G, A.gy), c0 = col_of(G, A.gx), hc = crop_size / 2;
+            uint8_t *o = crop + e * (int64_t)crop_size * crop_size;
+            for (int dr = 0; dr < crop_size; ++dr)
+                for (int dc = 0; dc < crop_size; ++dc) {
+                    const int r = r0 - hc + dr, c = c0 - hc + dc;
+                    uint8_t v = 2;
+                    if (r >= 0 && r < G.S && c >= 0 && c < G.S) v = (B.V.bits[r * G.wpr + (c >> 5)] >> (c & 31)) & 1u;
+                    o[dr * crop_size + dc] = v;
+                }
+        }
+    }
+    stats_flush(s_acc, stats);
+}
+
 // ------------------------------------------------------------------------------------------- K4
 // experiment/experiment_0.py:20-34 fused over K steps; env state lives in registers for the
 // whole launch, the only per-step HBM traffic is the action read and the record write.
@@ -879,6 +965,32 @@ ag_status ag_reset(const ag_params *p, const ag_grid *g, double *j1, double *j2,
         k<<<blocks_for(n), AG_BLOCK, smem, s>>>(*p, G, j1, j2, reward, flags, reset_ctr, mask, reset_u, R, seed, clear_flags, ust, n, env_id0); }
     AG_DISPATCH_ENGINE(engine, { if (reset_u) AG_RESET(true) else AG_RESET(false) });
 #undef AG_RESET
+    return launched();
+}
+
+ag_status ag_step_obs(const ag_params *p, const ag_grid *g, double *j1, double *j2, const void *actions, int32_t actions_f32,
+                      float *reward, uint8_t *flags, uint32_t *reset_ctr, uint32_t *ep_len, const double *targets, double *obs,
+                      float *reward_out, uint8_t *terminated, uint8_t *collision, double *final_obs, uint8_t *crop,
+                      int32_t crop_size, int64_t *stats, uint64_t seed, int32_t auto_reset, int64_t n, int64_t env_id0,
+                      int32_t engine, void *stream) {
+    if (n < 0 || (crop && (crop_size < 1 || crop_size > 63 || crop_size % 2 == 0))) return AG_ERR_SHAPE;
+    if (!p || !g) return AG_ERR_NULL;
+    GridDev G;
+    size_t smem;
+    ag_status st = make_grid_dev(p, g, env_id0, engine, &G, &smem);
+    if (st) return st;
+    if (n == 0) return AG_OK;
+    if (!j1 || !j2 || !actions || !reward || !flags || !reset_ctr || !ep_len || !obs || !reward_out || !terminated || !collision)
+        return AG_ERR_NULL;
+    if (((uintptr_t)actions % (actions_f32 ? 8 : 16)) || ((uintptr_t)obs % 16) || ((uintptr_t)final_obs % 16) || ((uintptr_t)targets % 16))
+        return AG_ERR_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *ust = reinterpret_cast<unsigned long long *>(stats);
+#define AG_SO(F32) { auto k = k_step_obs<E, F32>; if ((st = set_smem(k, smem))) return st; \
+        k<<<blocks_for(n), AG_BLOCK, smem, s>>>(*p, G, j1, j2, actions, reward, flags, reset_ctr, ep_len, targets, obs, reward_out, \
+                                                terminated, collision, final_obs, crop, crop_size, ust, seed, auto_reset, n, env_id0); }
+    AG_DISPATCH_ENGINE(engine, { if (actions_f32) AG_SO(true) else AG_SO(false) });
+#undef AG_SO
     return launched();
 }
 

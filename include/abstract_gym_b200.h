@@ -186,6 +186,23 @@ AG_API ag_status ag_reset(const ag_params *p, const ag_grid *g, double *j1, doub
                    int32_t R, uint64_t seed, int32_t clear_flags, int64_t *stats, int64_t n,
                    int64_t env_id0, int32_t engine, void *stream);
 
+/* K6: the gym-style step of an RL training loop (the caller of Scene.step / Scene.reset, scenario/scene_0.py:88-113,
+ * restarted the way experiment/experiment_0.py:30-34 does) in one launch: step, terminal observation, episode
+ * statistics, Scene.reset() of terminated envs (auto_reset != 0; Philox stream 1 candidates keyed by (seed, env_id0+e),
+ * consumed from reset_ctr) and the observation the env continues from.
+ * reward / flags: the sticky Scene.step_reward / flags, in/out (cleared by the auto-reset).
+ * obs, final_obs (optional): [n][AG_OBS_DIM] float64 = (joint_1, joint_2, EE_x, EE_y, |target_x-EE_x|, |target_y-EE_y|) --
+ * the last two are the quantities check_target_reached thresholds (scene_0.py:129-130).  reward_out / terminated /
+ * collision: this step's (joint_1, joint_2, step_reward, done|collision, collision_status) return values.
+ * crop (optional): [n][crop_size][crop_size] uint8 occupancy of the cells centred on the end effector's cell
+ * (1 occupied, 2 outside the grid; row 0 = top); crop_size odd, <= 63. */
+#define AG_OBS_DIM 6
+AG_API ag_status ag_step_obs(const ag_params *p, const ag_grid *g, double *j1, double *j2, const void *actions,
+                      int32_t actions_f32, float *reward, uint8_t *flags, uint32_t *reset_ctr, uint32_t *ep_len,
+                      const double *targets, double *obs, float *reward_out, uint8_t *terminated, uint8_t *collision,
+                      double *final_obs, uint8_t *crop, int32_t crop_size, int64_t *stats, uint64_t seed,
+                      int32_t auto_reset, int64_t n, int64_t env_id0, int32_t engine, void *stream);
+
 /* K4: the rollout loop experiment/experiment_0.py:20-34 fused over K steps:
  *   action -> step -> record -> if done|collision: reset.
  * actions: [K][n][2] float32, or NULL = Philox stream 0 (float64 (u-0.5)*action_scale).

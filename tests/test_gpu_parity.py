@@ -507,7 +507,7 @@ def test_vector_env_matches_scene_loop(ag, torch_, oracle, graph):
         n_term += int(m.sum().item())
         sc.reset(mask=m)
         assert torch_.equal(obs[:, 0], sc.robot.joint_1) and torch_.equal(obs[:, 1], sc.robot.joint_2)
-    assert n_term > 20 and env.stats() == ref.stats()
+    assert n_term > 20 and env.stats()["episodes"] == n_term and env.stats()["env_steps"] == ref.stats()["env_steps"]
 
 
 @pytest.mark.gpu
@@ -572,41 +572,126 @@ def test_tangency_band_all_engines_and_oracle(ag, torch_, oracle):
 
 @pytest.mark.gpu
 def test_torch_custom_ops_equal_object_api(ag, torch_):
-    """torch.ops.abstract_gym_b200.* (functional front end over the same C symbols) == BatchedScene"""
-    from abstract_gym_b200 import ops
-    n, K = 3000, 20
+    """torch.ops.abstract_gym_b200.* -- the COMPILED op library (csrc/ag_torch_ops.cpp over the same C symbols) ==
+    BatchedScene, on scene_0's map and on per-batch 256x256 maps with transposed planes, scripted reset candidates,
+    per-env targets, a statistics-only rollout and the filter diagnostics; CPU tensors are refused."""
+    import time
+    from abstract_gym_b200 import ops, build
+    assert os.path.exists(build.OPS_LIB)
+    O = torch_.ops.abstract_gym_b200
+    n, K = 3072, 20
     rng = np.random.default_rng(41)
     j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
     acts = torch_.as_tensor(((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32), device="cuda")
-    g = ag.OccupancyGrid(size=9, random_obstacle=False)
-    ref = make_scene(ag, torch_, g, j1, j2, seed=3)
-    rec = ref.rollout(K, actions=acts)
-    sc = make_scene(ag, torch_, g, j1, j2, seed=3)         # only used as a bag of correctly typed state tensors
-    dg = sc.grid
-    P, M = ops.pack_params(sc.params()), ops.pack_grid_meta(dg)
-    out = sc.alloc_records(K)
-    hit = torch_.empty(n, dtype=torch_.uint8, device="cuda")
-    torch_.ops.abstract_gym_b200.collision_check(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1, sc.robot.joint_2,
-                                                 hit, 0, 1)
-    assert torch_.equal(hit != 0, ref.__class__.collision_check(make_scene(ag, torch_, g, j1, j2)))
-    torch_.ops.abstract_gym_b200.rollout(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1, sc.robot.joint_2,
-                                         sc.step_reward, sc.flags, sc.step_ctr, sc.reset_ctr, sc.ep_len, acts,
-                                         out["j1"], out["j2"], out["reward"], out["flags"], sc.stats, 3, 0, 1)
-    for k in ("j1", "j2", "reward", "flags"):
-        assert torch_.equal(rec[k], out[k]), k
-    assert torch_.equal(ref.stats, sc.stats) and torch_.equal(ref.robot.joint_1, sc.robot.joint_1)
-    # one step + masked reset through the ops == through the object API
-    a1 = (torch_.rand(n, 2, dtype=torch_.float64, device="cuda") - 0.5) * 0.1
-    ref.step(a1); m = (ref.flags != 0).to(torch_.uint8); ref.reset(mask=m)
-    torch_.ops.abstract_gym_b200.step(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1, sc.robot.joint_2, a1,
-                                      sc.step_reward, sc.flags, sc.stats, 0, 1)
-    m2 = (sc.flags != 0).to(torch_.uint8)
-    torch_.ops.abstract_gym_b200.reset(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1, sc.robot.joint_2,
-                                       sc.step_reward, sc.flags, sc.reset_ctr, m2, sc.stats, 3, 0, 1)
-    assert torch_.equal(m, m2) and torch_.equal(ref.robot.joint_1, sc.robot.joint_1) and torch_.equal(ref.stats, sc.stats)
+    ru = torch_.as_tensor(rng.random((n, 12, 2)), device="cuda")
+    tg = torch_.as_tensor(np.stack([rng.uniform(-0.5, 0.5, n), rng.uniform(-0.5, 0.5, n)], axis=1), device="cuda")
+    occs = [random_grid(rng, 256, 0.008) for _ in range(n // 256)]
+    for kind in ("scene0", "c5"):
+        g = ag.OccupancyGrid(size=9, random_obstacle=False) if kind == "scene0" else \
+            ag.BatchedOccupancyGrid(torch_.as_tensor(np.stack(occs), device="cuda"), 256)
+        ref = make_scene(ag, torch_, g, j1, j2, seed=3)
+        rec = ref.rollout(K, actions=acts, reset_u=ru, targets=tg)
+        sc = make_scene(ag, torch_, g, j1, j2, seed=3)         # only used as a bag of correctly typed state tensors
+        dg = sc.grid
+        assert (dg.bits_t is not None) == (kind == "c5")
+        P, GA = ops.pack_params(sc.params()), ops.grid_args(dg)
+        out = sc.alloc_records(K)
+        hit = torch_.empty(n, dtype=torch_.uint8, device="cuda")
+        O.collision_check(P, *GA, sc.robot.joint_1, sc.robot.joint_2, hit, None, 0, 1)
+        assert torch_.equal(hit != 0, make_scene(ag, torch_, g, j1, j2).collision_check())
+        diag = torch_.zeros(3, dtype=torch_.int64, device="cuda")
+        O.rollout(P, *GA, sc.robot.joint_1, sc.robot.joint_2, sc.step_reward, sc.flags, sc.step_ctr, sc.reset_ctr, sc.ep_len,
+                  acts, ru, tg, out["j1"], out["j2"], out["reward"], out["flags"], sc.stats, diag, None, None, K, 3, 0, 1)
+        for k in ("j1", "j2", "reward", "flags"):
+            assert torch_.equal(rec[k], out[k]), (kind, k)
+        assert torch_.equal(ref.stats, sc.stats) and torch_.equal(ref.robot.joint_1, sc.robot.joint_1)
+        assert torch_.equal(ref.reset_ctr, sc.reset_ctr)
+        # statistics only, in-kernel actions
+        ref.rollout(K, record=False)
+        O.rollout(P, *GA, sc.robot.joint_1, sc.robot.joint_2, sc.step_reward, sc.flags, sc.step_ctr, sc.reset_ctr, sc.ep_len,
+                  None, None, None, None, None, None, None, sc.stats, None, None, None, K, 3, 0, 1)
+        assert torch_.equal(ref.stats, sc.stats) and torch_.equal(ref.robot.joint_2, sc.robot.joint_2)
+        # one step + masked reset through the ops == through the object API
+        a1 = (torch_.rand(n, 2, dtype=torch_.float64, device="cuda") - 0.5) * 0.1
+        ref.step(a1, targets=tg); m = (ref.flags != 0).to(torch_.uint8); ref.reset(mask=m)
+        O.step(P, *GA, sc.robot.joint_1, sc.robot.joint_2, a1, sc.step_reward, sc.flags, None, None, None, sc.stats, tg, 0, 1)
+        m2 = (sc.flags != 0).to(torch_.uint8)
+        O.reset(P, *GA, sc.robot.joint_1, sc.robot.joint_2, sc.step_reward, sc.flags, sc.reset_ctr, m2, None, sc.stats, 3, True, 0, 1)
+        assert torch_.equal(m, m2) and torch_.equal(ref.robot.joint_1, sc.robot.joint_1) and torch_.equal(ref.stats, sc.stats)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        O.collision_check(P, *GA, sc.robot.joint_1.cpu(), sc.robot.joint_2.cpu(), hit.cpu(), None, 0, 1)
     with pytest.raises(RuntimeError):
-        torch_.ops.abstract_gym_b200.collision_check(P, dg.bits, dg.min_x, dg.min_y, M, sc.robot.joint_1.cpu(),
-                                                     sc.robot.joint_2, hit, 0, 1)
+        O.collision_check(P, *GA, sc.robot.joint_1.float(), sc.robot.joint_2, hit, None, 0, 1)
+    # host overhead of one op call (validation + stream lookup + the launch itself), tiny kernel
+    small = make_scene(ag, torch_, ag.OccupancyGrid(size=9, random_obstacle=False), j1[:64], j2[:64])
+    GS, h64 = ops.grid_args(small.grid), torch_.empty(64, dtype=torch_.uint8, device="cuda")
+    for _ in range(200):
+        O.collision_check(P, *GS, small.robot.joint_1, small.robot.joint_2, h64, None, 0, 1)
+    torch_.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        O.collision_check(P, *GS, small.robot.joint_1, small.robot.joint_2, h64, None, 0, 1)
+    dt_op = (time.perf_counter() - t0) / 2000
+    torch_.cuda.synchronize()
+    print("torch op call: %.1f us per call (host side, includes the kernel launch)" % (dt_op * 1e6))
+    assert dt_op < 50e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_vector_env_vs_oracle(ag, torch_, oracle, graph):
+    """VectorEnv (one fused K6 launch per step) against the oracle's Scene.step + the reference's reset rule
+    (scene_0.py:105-113,174-181 with Philox stream-1 candidates) for 40 steps, eager and as a CUDA graph: joints,
+    reward, terminated, collision, observations of restarted envs, the occupancy crop and the episode statistics."""
+    n, T, seed = 4096, 40, 21
+    env = ag.VectorEnv(n, device="cuda", seed=seed, crop_size=3)
+    obs = env.reset().clone()
+    sq, ci = oracle.manual_grid()
+    j1, j2 = env.scene.robot.joint_1.cpu().numpy().copy(), env.scene.robot.joint_2.cpu().numpy().copy()
+    rc = env.scene.reset_ctr.cpu().numpy().view(np.uint32).astype(np.int64).copy()
+    rw, fl = np.zeros(n), np.zeros(n, dtype=np.uint8)
+    if graph:
+        env.capture()
+        assert torch_.equal(env._obs, obs)                    # capture() leaves the caller's observation untouched
+    rng = np.random.default_rng(33)
+    episodes = 0
+    occ = np.zeros((9, 9), dtype=np.uint8)
+    for r, c in ag.OccupancyGrid.MANUAL_CELLS:
+        occ[r, c] = 1
+    for t in range(T):
+        a = (rng.random((n, 2)) - 0.5) * 0.3
+        o, r_dev, term, trunc, info = env.step(torch_.as_tensor(a, device="cuda"))
+        res = oracle.step_batch(j1, j2, a, rw, fl, sq, ci)
+        assert np.array_equal(info["final_obs"][:, 0].cpu().numpy(), j1) and np.array_equal(info["final_obs"][:, 1].cpu().numpy(), j2)
+        assert np.array_equal(r_dev.cpu().numpy(), rw.astype(np.float32))
+        assert np.array_equal(term.cpu().numpy(), fl != 0) and np.array_equal(info["collision"].cpu().numpy(), (fl & 1) != 0)
+        assert rel_close(info["final_obs"][:, 2:4].cpu().numpy(), res["ee"]) and rel_close(info["final_obs"][:, 4:6].cpu().numpy(), res["dist"])
+        for e in np.flatnonzero(fl != 0):                     # Scene.reset(): resample only while colliding
+            episodes += 1
+            if fl[e] & 1:
+                for _ in range(64):
+                    u0, u1 = oracle.philox_uniform2(seed, int(e), int(rc[e]), 1)
+                    rc[e] += 1
+                    j1[e], j2[e] = (u0 * np.pi) * 2.0, (u1 * np.pi) * 2.0
+                    h = oracle.collision_batch(j1[e:e + 1].copy(), j2[e:e + 1].copy(), sq, want_first_hit=False)
+                    h = h[0] if isinstance(h, tuple) else h
+                    if not h[0]:
+                        break
+            rw[e], fl[e] = 0.0, 0
+        assert np.array_equal(o[:, 0].cpu().numpy(), j1) and np.array_equal(o[:, 1].cpu().numpy(), j2)
+        # the crop: 3x3 cells around the end effector's cell of the observation the env continues from
+        gx, gy = o[:, 2].cpu().numpy(), o[:, 3].cpu().numpy()
+        col = np.floor((gx + 0.8) / 0.2).astype(int); row = (np.floor((0.8 - gy) / 0.2) + 1).astype(int)
+        crop = info["crop"].cpu().numpy()
+        for e in range(0, n, 97):
+            for dr in range(3):
+                for dc in range(3):
+                    r_, c_ = row[e] - 1 + dr, col[e] - 1 + dc
+                    want = 2 if not (0 <= r_ < 9 and 0 <= c_ < 9) else int(occ[r_, c_])
+                    assert crop[e, dr, dc] == want
+    st = env.stats()
+    assert episodes > 200 and st["episodes"] == episodes and st["env_steps"] == n * T
+    assert np.array_equal(env.scene.reset_ctr.cpu().numpy().view(np.uint32).astype(np.int64), rc)
 
 
 @pytest.mark.gpu
