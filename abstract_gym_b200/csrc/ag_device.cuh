@@ -147,6 +147,30 @@ __device__ __forceinline__ int col_of(const GridDev &G, double x) {
     return (int)fmin(fmax(f, -1.0), (double)G.S);
 }
 
+// ---------------------------------------------------------------- one link against every occupied cell
+// scenario/scene_0.py:67-75 for one link: the reference's own loop.  Used by link_exact for nearly axis-aligned links.
+template <bool WANT_FIRST>
+__device__ __noinline__ bool link_brute(const GridDev &G, const GridView &V, double p0x, double p0y, double p1x, double p1y,
+                                        double eps, int &fh, int &axis) {
+    const LineD L = make_line(p0x, p0y, p1x, p1y);
+    bool hit = false;
+    for (int r = 0; r < G.S; ++r)
+        for (int w = 0; w < G.wpr; ++w) {
+            uint32_t word = V.bits[r * G.wpr + w];
+            while (word) {
+                const int c = (w << 5) + __ffs(word) - 1;
+                word &= word - 1;
+                const double mnx = V.min_x[c], mny = V.min_y[r];
+                if (segment_square_exact(L, mnx, mny, __dadd_rn(mnx, G.side), __dadd_rn(mny, G.side), eps, axis)) {
+                    if (!WANT_FIRST) return true;
+                    hit = true;
+                    fh = min(fh, r * G.S + c);
+                }
+            }
+        }
+    return hit;
+}
+
 // ---------------------------------------------------------------- EXACT engine: one link
 // Conservative traversal: every cell whose closed square comes within G.margin of the segment
 // is visited (a superset of the cells the reference can flag, because a hit needs a point of
@@ -155,6 +179,11 @@ __device__ __forceinline__ int col_of(const GridDev &G, double x) {
 template <bool WANT_FIRST>
 __device__ __forceinline__ bool link_exact(const GridDev &G, const GridView &V, double p0x, double p0y, double p1x,
                                            double p1y, double eps, int &fh, int &axis) {
+    // A nearly axis-aligned link (|dx| or |dy| < 1e-7 m): the reference's lam = (x - p0.x) / (p1.x - p0.x)
+    // (collision_checker.py:79-80,90-91) then carries rounding noise of ~ulp/|dx|, which can move its accepted range far
+    // beyond the segment's end, i.e. outside any bounded neighbourhood of the link.  Probability ~1e-7 per link and
+    // step: take the reference's own loop over every occupied cell.
+    if (fmin(fabs(p1x - p0x), fabs(p1y - p0y)) < 1.0e-7) return link_brute<WANT_FIRST>(G, V, p0x, p0y, p1x, p1y, eps, fh, axis);
     const double m = G.margin;
     int r_lo = row_of(G, fmax(p0y, p1y) + m), r_hi = row_of(G, fmin(p0y, p1y) - m);
     if (r_lo > G.S - 1 || r_hi < 0) return false;

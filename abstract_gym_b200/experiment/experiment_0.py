@@ -133,22 +133,38 @@ class Trajectories:
         return n
 
 
-def run_experiment(scene, steps, chunk_steps=64, generator=None, actions=None, keep_on_host=True):
-    """experiment_0.py:20-34 for every env of `scene` with the fused rollout kernel, `chunk_steps` steps per launch.
-    Actions are (u-0.5)*0.1 uniforms drawn on the device (or `actions` [steps,N,2] float32).  Returns Trajectories
-    (joints as float32) -- the trajectory sink of the fast path."""
+def run_experiment(scene, steps, chunk_steps=64, actions=None, pipeline_steps=4):
+    """experiment_0.py:20-34 for every env of `scene` with the fused rollout kernel, `chunk_steps` steps per call, the
+    records streamed to pinned host memory by the pipelined host path (copies overlap the kernels):
+
+      * actions=None  -- the actions are drawn in the kernel (Philox stream 0, float64 (u-0.5)*0.1); nothing goes host ->
+        device, the joint planes stream out and reward / flags arrive as an event list (`rollout_events_host`); the
+        recorded actions a0 / a1 are reproduced on the host from the draw counters (`philox_actions`);
+      * actions [steps,N,2] float32 -- host actions in, the four record planes out (`rollout_host`).
+
+    Returns Trajectories (joints as float32) -- the trajectory sink of the fast path."""
     import torch
     parts, t = [], 0
     while t < steps:
         k = min(chunk_steps, steps - t)
         if actions is None:
-            act = ((torch.rand(k, scene.n, 2, device=scene.device, generator=generator) - 0.5) * 0.1).to(torch.float32)
+            sc0 = scene.step_ctr.cpu().numpy().view(np.uint32).astype(np.uint64)
+            sink = scene.alloc_event_sink(k, pinned_host=True)
+            scene.rollout_events_host(k, sink, chunk_steps=pipeline_steps)
+            if sink["count"] > sink["events"].shape[0]:
+                raise RuntimeError("event sink overflow: %d events, capacity %d" % (sink["count"], sink["events"].shape[0]))
+            reward, flags = scene.events_to_planes(sink, k)
+            act = scene.philox_actions(np.arange(scene.n), sc0, k)
+            parts.append(Trajectories(sink["j1"].numpy().copy(), sink["j2"].numpy().copy(), act[..., 0], act[..., 1], reward, flags))
         else:
-            act = torch.as_tensor(actions[t:t + k], device=scene.device).to(torch.float32)
-        rec = scene.rollout(k, actions=act)
-        parts.append(Trajectories.from_rollout(rec, act) if keep_on_host else (rec, act))
+            hact = torch.empty(k, scene.n, 2, dtype=torch.float32, pin_memory=True)
+            hact.copy_(torch.as_tensor(np.asarray(actions[t:t + k], dtype=np.float32)))
+            hout = scene.alloc_records(k, pinned_host=True)
+            scene.rollout_host(k, hact, hout, chunk_steps=pipeline_steps)
+            parts.append(Trajectories(hout["j1"].numpy().copy(), hout["j2"].numpy().copy(), hact[..., 0].numpy().copy(),
+                                      hact[..., 1].numpy().copy(), hout["reward"].numpy().copy(), hout["flags"].numpy().copy()))
         t += k
-    return Trajectories.concatenate(parts) if keep_on_host else parts
+    return Trajectories.concatenate(parts)
 
 
 def run_experiment_exact(scene, steps, actions=None, generator=None, reset_u=None):

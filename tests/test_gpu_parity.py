@@ -454,6 +454,12 @@ def test_experiment_drivers_fast_equals_exact(ag, torch_):
     assert np.array_equal(fast.flags, exact.flags) and np.array_equal(fast.reward, exact.reward)
     assert np.array_equal(fast.j1, exact.j1.astype(np.float32)) and np.array_equal(fast.j2, exact.j2.astype(np.float32))
     assert fast.episode_index().tolist() == exact.episode_index().tolist() and len(fast.episode_index()) > 20
+    # in-kernel actions through the zero-H2D event path: the recorded float64 actions replay to the same episodes
+    fast2 = run_experiment(make_scene(ag, torch_, g, j1, j2, seed=6), K, chunk_steps=16)
+    acts64 = np.stack([fast2.a0, fast2.a1], axis=-1)
+    exact2 = run_experiment_exact(make_scene(ag, torch_, g, j1, j2, seed=6), K, actions=acts64)
+    assert np.array_equal(fast2.flags, exact2.flags) and np.array_equal(fast2.reward, exact2.reward)
+    assert np.array_equal(fast2.j1, exact2.j1.astype(np.float32)) and len(fast2.episode_index()) > 20
 
 
 @pytest.mark.gpu
@@ -1145,3 +1151,33 @@ def test_exact_rollout_with_large_staged_grids(ag, torch_, oracle, S, p):
     occ[S // 2 - 3:S // 2 + 4, S // 2 - 3:S // 2 + 4] = 0
     for engine in ("exact", "fast"):
         _rollout_case(ag, torch_, oracle, [occ], 768, 6, engine, True, seed=8)
+
+
+@pytest.mark.gpu
+def test_nearly_axis_aligned_links_exact_brute_oracle(ag, torch_, oracle):
+    """Links within 1e-16 .. 1e-7 rad of an axis: the reference's lambda arithmetic (collision_checker.py:79-91) divides
+    by dx ~ 1e-13 there and may accept a square on the link's infinite line far beyond its end.  EXACT switches to the
+    reference's loop over every occupied cell for such links, so EXACT == BRUTE == oracle also here."""
+    rng = np.random.default_rng(91)
+    n = 1 << 16
+    occ = np.zeros((31, 31), dtype=np.uint8)
+    occ[2:6, 14:17] = 1; occ[25:29, 14:17] = 1; occ[14:17, 2:6] = 1; occ[14:17, 25:29] = 1     # squares on both axes, far from the arm
+    occ[rng.integers(0, 31, 40), rng.integers(0, 31, 40)] = 1
+    occ[13:18, 13:18] = 0
+    axis = rng.integers(0, 4, n) * (np.pi / 2)
+    delta = 10.0 ** rng.uniform(-16, -7, n) * rng.choice([-1.0, 1.0], n)
+    j1 = axis + delta
+    j2 = np.where(rng.random(n) < 0.5, rng.integers(0, 4, n) * (np.pi / 2) + np.roll(delta, 1), rng.uniform(0, 2 * np.pi, n))
+    sq = oracle.grid_squares(occ)[0]
+    ref = oracle.collision_batch(j1, j2, sq, want_first_hit=False)
+    ref = (ref[0] if isinstance(ref, tuple) else ref) != 0
+    hits = {}
+    for engine in ("exact", "brute", "fast"):
+        sc = make_scene(ag, torch_, occ, j1, j2, engine=engine)
+        hits[engine] = sc.collision_check().cpu().numpy()
+    assert np.array_equal(hits["exact"], hits["brute"])
+    bad = np.flatnonzero(hits["exact"] != ref)
+    # CUDA sincos vs glibc in the last ulp moves dx by ~1e-17: only poses whose flag flips under that are excused
+    assert len(bad) <= n // 200, "%d mismatches vs the oracle" % len(bad)
+    print("near-axis links: exact==brute on %d poses; %d differ from the CPU oracle (sincos ulp), fast differs from exact on %d"
+          % (n, len(bad), int((hits["fast"] != hits["exact"]).sum())))
