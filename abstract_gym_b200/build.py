@@ -2,7 +2,9 @@
 
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the gpurun snapshot.
 Every translation unit is compiled to an object file in parallel, then linked.
-Usage:  python -m abstract_gym_b200.build [--force] [--verbose] [--out PATH]
+Usage:  python -m abstract_gym_b200.build [--force] [--verbose] [--out PATH] [--debug]
+--debug builds libabstract_gym_b200_debug.so with -DAG_DEBUG_BOUNDS (device-side index assertions; load it with
+AG_LIB_PATH=<that file>); the release library is untouched.
 """
 import concurrent.futures
 import os
@@ -17,6 +19,7 @@ LIB = os.environ.get("AG_LIB_PATH") or os.path.join(HERE, "libabstract_gym_b200.
 SOURCES = ["ag_kernels.cu", "ag_rollout_lut.cu", "ag_dense.cu", "ag_host.cu"]
 HEADERS = ["ag_device.cuh", "ag_fast.cuh", "ag_rollout.cuh", os.path.join(INCLUDE, "abstract_gym_b200.h")]
 OBJDIR = os.path.join(HERE, "build")
+DEBUG_LIB = os.path.join(HERE, "libabstract_gym_b200_debug.so")
 # the compiled torch custom-op library (torch.ops.abstract_gym_b200.*): a C++ shim over the C ABI, linked against
 # libabstract_gym_b200.so (rpath $ORIGIN) and the torch libraries of the running interpreter
 OPS_LIB = os.path.join(HERE, "libabstract_gym_b200_ops.so")
@@ -41,22 +44,31 @@ def sources():
     return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-def needs_build() -> bool:
-    if os.environ.get("AG_LIB_PATH"):
-        return False
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
+def _stale(lib) -> bool:
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, s) for s in sources()] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     deps.append(os.path.abspath(__file__))
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False, out: str = None) -> str:
+def needs_build() -> bool:
+    if os.environ.get("AG_LIB_PATH"):
+        return False
+    return not os.path.exists(LIB) or _stale(LIB)
+
+
+def build_debug(force: bool = False, verbose: bool = False) -> str:
+    """the -DAG_DEBUG_BOUNDS library (csrc/ag_device.cuh AG_CHECK_INDEX); tests/test_gpu_parity.py runs a subset on it"""
+    if not force and os.path.exists(DEBUG_LIB) and not _stale(DEBUG_LIB):
+        return DEBUG_LIB
+    return build(verbose=verbose, out=DEBUG_LIB, defines=["-DAG_DEBUG_BOUNDS"])
+
+
+def build(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
     if out is None and not force and not needs_build():
         return LIB
     nvcc = find_nvcc()
-    extra = os.environ.get("AG_NVCC_EXTRA", "").split()          # A/B builds, e.g. -DAG_LUT_BITS=10
+    extra = os.environ.get("AG_NVCC_EXTRA", "").split() + list(defines)      # A/B builds, e.g. -DAG_LUT_B1=10
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
     target = out or LIB
     objdir = OBJDIR if out is None else target + ".obj"
@@ -128,6 +140,9 @@ def build_ops(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
+    if "--debug" in sys.argv:
+        print(build_debug(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+        sys.exit(0)
     out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out))
     if out is None:

@@ -4,6 +4,7 @@
 // __dmul_rn / __ddiv_rn are never contracted into FMAs), in the reference's operation order.
 // Reference citations are file:line relative to the reference root.
 #pragma once
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -135,6 +136,24 @@ __device__ __forceinline__ bool segment_square_exact(const LineD &L, double min_
     return (1.0 > lam1 && lam1 > eps) || (1.0 > lam2 && lam2 > eps);   // :82
 }
 
+// ---------------------------------------------------------------- debug build: index assertions
+// `python -m abstract_gym_b200.build --debug` compiles libabstract_gym_b200_debug.so with -DAG_DEBUG_BOUNDS: every
+// computed index into the bit grid, the cell-corner arrays, the record planes, the action rows and the event sink is
+// checked on the device and a violation traps the kernel (the launch then fails with a CUDA error, which the host entry
+// reports).  The release build compiles the checks away.
+#ifdef AG_DEBUG_BOUNDS
+#define AG_CHECK_INDEX(i, n)                                                                                          \
+    do {                                                                                                              \
+        if (!((long long)(i) >= 0 && (long long)(i) < (long long)(n))) {                                              \
+            printf("AG_DEBUG_BOUNDS %s:%d: index %lld outside [0, %lld)\n", __FILE__, __LINE__, (long long)(i),        \
+                   (long long)(n));                                                                                   \
+            __trap();                                                                                                 \
+        }                                                                                                             \
+    } while (0)
+#else
+#define AG_CHECK_INDEX(i, n) ((void)0)
+#endif
+
 // ---------------------------------------------------------------- cell index helpers
 // Row r spans y in [E/2 - r*s, E/2 - (r-1)*s]; column c spans x in [c*s - E/2, (c+1)*s - E/2]
 // (environment/occupancy_grid.py:59-67: S cells of side E/(S-1), y flipped, not centred).
@@ -160,6 +179,7 @@ __device__ __noinline__ bool link_brute(const GridDev &G, const GridView &V, dou
             while (word) {
                 const int c = (w << 5) + __ffs(word) - 1;
                 word &= word - 1;
+                AG_CHECK_INDEX(c, G.S);      // padding bits of the last word of a row must be clear
                 const double mnx = V.min_x[c], mny = V.min_y[r];
                 if (segment_square_exact(L, mnx, mny, __dadd_rn(mnx, G.side), __dadd_rn(mny, G.side), eps, axis)) {
                     if (!WANT_FIRST) return true;
@@ -208,10 +228,12 @@ __device__ __forceinline__ bool link_exact(const GridDev &G, const GridView &V, 
             uint32_t mask = 0xFFFFFFFFu;
             if (w == (c_lo >> 5)) mask &= 0xFFFFFFFFu << (c_lo & 31);
             if (w == (c_hi >> 5)) mask &= 0xFFFFFFFFu >> (31 - (c_hi & 31));
+            AG_CHECK_INDEX(r * G.wpr + w, G.S * G.wpr);
             uint32_t word = V.bits[r * G.wpr + w] & mask;
             while (word) {
                 const int c = (w << 5) + __ffs(word) - 1;
                 word &= word - 1;
+                AG_CHECK_INDEX(c, G.S);
                 if (!have_line) { L = make_line(p0x, p0y, p1x, p1y); have_line = true; }
                 const double mnx = V.min_x[c], mny = V.min_y[r];
                 if (segment_square_exact(L, mnx, mny, __dadd_rn(mnx, G.side), __dadd_rn(mny, G.side), eps, axis)) {
@@ -239,6 +261,7 @@ __device__ __forceinline__ bool arm_brute(const GridDev &G, const GridView &V, c
             while (word) {
                 const int c = (w << 5) + __ffs(word) - 1;
                 word &= word - 1;
+                AG_CHECK_INDEX(c, G.S);      // padding bits of the last word of a row must be clear
                 const double mnx = V.min_x[c], mny = V.min_y[r];
                 const double mxx = __dadd_rn(mnx, G.side), mxy = __dadd_rn(mny, G.side);
                 if (segment_square_exact(L1, mnx, mny, mxx, mxy, eps, axis) ||

@@ -359,8 +359,10 @@ __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, co
         // few lines, or (no transposed copy) a shallow link walked by rows: every line gets the whole position range
         const int p_lo = max(round_magic(pseg_lo - mcell), 0), p_hi = min(round_magic(pseg_hi + mcell), S1);
         if (p_lo > p_hi) return 0;
-        for (int l = l_lo; l <= l_hi; ++l, linep += G.wpr)
+        for (int l = l_lo; l <= l_hi; ++l, linep += G.wpr) {
+            AG_CHECK_INDEX(l, G.S); AG_CHECK_INDEX(p_lo, G.S); AG_CHECK_INDEX(p_hi, G.S);
             if (scan_line(V, linep, l, p_lo, p_hi, K)) return 1;
+        }
         return K.result;
     }
     // One line per iteration, the position interval follows the link incrementally: along the link p is linear in
@@ -379,6 +381,8 @@ __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, co
         pprev = pcur;
         const int p_lo = max(round_magic(lo), 0), p_hi = min(round_magic(hi), S1);
         if (p_lo > p_hi) continue;
+        AG_CHECK_INDEX(l, G.S); AG_CHECK_INDEX(p_lo, G.S); AG_CHECK_INDEX(p_hi, G.S);
+        AG_CHECK_INDEX(linep - (K.swapped ? V.bits_t : V.bits) + (p_hi >> 5), G.S * G.wpr);
         if (scan_line(V, linep, l, p_lo, p_hi, K)) return 1;
     }
     return K.result;

@@ -38,6 +38,7 @@ __device__ __forceinline__ void emit_event(const RolloutDev &A, int64_t e, int t
     if (A.events != nullptr && (fl != 0 || rw != 0.0f)) {
         const unsigned long long i = atomicAdd(A.event_count, 1ull);
         if (i < (unsigned long long)A.event_cap) {
+            AG_CHECK_INDEX(t, A.K); AG_CHECK_INDEX(A.event_step0 + t, 1 << 24);
             A.events[3 * i] = (uint32_t)e;
             A.events[3 * i + 1] = ((uint32_t)(A.event_step0 + t) << 8) | (fl & 0xFFu);
             A.events[3 * i + 2] = __float_as_uint(rw);
@@ -158,6 +159,7 @@ __device__ __forceinline__ GridView thread_view(const GridDev &G, unsigned char 
 template <bool RECORD>
 __device__ __forceinline__ void store_record(const RolloutDev &A, int64_t o, double q1, double q2, float rw, uint32_t fl) {
     if (RECORD) {
+        AG_CHECK_INDEX(o, (int64_t)(A.K - 1) * A.row_stride + A.n);
         __stcs(A.rec_j1 + o, (float)q1);
         __stcs(A.rec_j2 + o, (float)q2);
         if (A.rec_reward != nullptr) {                  // joints-only records: reward / flags go to the event sink
@@ -173,6 +175,7 @@ __device__ __forceinline__ void store_record(const RolloutDev &A, int64_t o, dou
 template <bool RECORD>
 __device__ __forceinline__ void store_uneventful(const RolloutDev &A, int64_t o, double q1, double q2) {
     if (RECORD) {
+        AG_CHECK_INDEX(o, (int64_t)(A.K - 1) * A.row_stride + A.n);
         __stcs(A.rec_j1 + o, (float)q1);
         __stcs(A.rec_j2 + o, (float)q2);
         if (!A.zfill && A.rec_reward != nullptr) {

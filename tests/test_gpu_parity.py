@@ -1181,3 +1181,74 @@ def test_nearly_axis_aligned_links_exact_brute_oracle(ag, torch_, oracle):
     assert len(bad) <= n // 200, "%d mismatches vs the oracle" % len(bad)
     print("near-axis links: exact==brute on %d poses; %d differ from the CPU oracle (sincos ulp), fast differs from exact on %d"
           % (n, len(bad), int((hits["fast"] != hits["exact"]).sum())))
+
+
+_DEBUG_CHILD = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+import abstract_gym_b200 as ag
+from abstract_gym_b200 import _lib
+from oracle import oracle as orc
+assert _lib.lib_path().endswith("_debug.so"), _lib.lib_path()
+mode = sys.argv[1]
+rng = np.random.default_rng(11)
+if mode == "parity":
+    n, K = 2048, 10
+    cases = [("scene0", None, 9),
+             ("rand64", [(rng.random((64, 64)) < 0.02).astype(np.uint8)], 64),
+             ("rand300", [(rng.random((300, 300)) < 0.004).astype(np.uint8) for _ in range(2)], 300)]
+    for name, occs, S in cases:
+        for engine in ("fast", "exact", "brute"):
+            if engine == "brute" and S > 64:
+                continue
+            j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+            if occs is None:
+                grid, squares, epg = ag.OccupancyGrid(size=9, random_obstacle=False), [orc.manual_grid()[0]], None
+            else:
+                epg = n // len(occs)
+                grid = ag.BatchedOccupancyGrid(torch.as_tensor(np.stack(occs), device="cuda"), epg)
+                squares = [orc.grid_squares(o)[0] for o in occs]
+            robot = ag.BatchedTwoJointRobot(torch.as_tensor(j1, device="cuda"), torch.as_tensor(j2, device="cuda"))
+            sc = ag.BatchedScene(robot, grid, engine=engine, seed=4)
+            rec = sc.rollout(K)
+            torch.cuda.synchronize()
+            st = orc.RolloutState(j1, j2)
+            kw = {} if epg is None else dict(envs_per_grid=epg)
+            orec, ostats = orc.rollout(st, K, squares, seed=4, **kw)
+            assert np.array_equal(rec["flags"].cpu().numpy(), orec["flags"]), (name, engine)
+            assert np.array_equal(sc.stats.cpu().numpy(), ostats), (name, engine)
+            assert np.array_equal(sc.robot.joint_1.cpu().numpy(), st.j1), (name, engine)
+    print("debug parity ok")
+else:
+    # a malformed bit grid: a padding bit (column 31 of a 9-column map) is set.  The release build would read a cell
+    # corner past the end of the array; the debug build must stop the kernel.
+    grid = ag.OccupancyGrid(size=9, random_obstacle=False)
+    j = torch.zeros(64, dtype=torch.float64, device="cuda")
+    sc = ag.BatchedScene(ag.BatchedTwoJointRobot(j.clone(), j.clone()), grid, engine="brute", seed=1)
+    sc.grid.bits.view(torch.int32).view(-1)[0] |= -(1 << 31)
+    try:
+        sc.collision_check()
+        torch.cuda.synchronize()
+    except Exception as e:
+        print("trapped:", type(e).__name__)
+        sys.exit(3)
+    print("not trapped")
+'''
+
+
+@pytest.mark.gpu
+def test_debug_bounds_build(ag, torch_):
+    """the -DAG_DEBUG_BOUNDS library (csrc/ag_device.cuh AG_CHECK_INDEX): same results as the oracle on list, traversal
+    and brute paths with every index assertion compiled in, and a malformed grid stops the kernel"""
+    import subprocess
+    import sys
+    from abstract_gym_b200 import build as ag_build
+    lib = ag_build.build_debug()
+    code = _DEBUG_CHILD % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AG_LIB_PATH=lib)
+    r = subprocess.run([sys.executable, "-c", code, "parity"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "debug parity ok" in r.stdout, r.stdout[-3000:]
+    r = subprocess.run([sys.executable, "-c", code, "trap"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=300)
+    assert r.returncode == 3 and "AG_DEBUG_BOUNDS" in r.stdout and "trapped" in r.stdout, r.stdout[-3000:]
