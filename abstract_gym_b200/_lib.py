@@ -11,7 +11,7 @@ from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 ENGINE_EXACT, ENGINE_FAST, ENGINE_BRUTE = 0, 1, 2
 ENGINES = {"exact": ENGINE_EXACT, "fast": ENGINE_FAST, "brute": ENGINE_BRUTE}
 FLAG_COLLISION, FLAG_DONE = 1, 2
@@ -44,7 +44,8 @@ class Grid(C.Structure):
     _fields_ = [("bits", C.c_void_p), ("min_x", C.c_void_p), ("min_y", C.c_void_p),
                 ("side", C.c_double), ("env_size", C.c_double),
                 ("S", C.c_int32), ("words_per_row", C.c_int32), ("n_grids", C.c_int32), ("max_occupied", C.c_int32),
-                ("grid_stride_words", C.c_int64), ("envs_per_grid", C.c_int64), ("bits_t", C.c_void_p)]
+                ("grid_stride_words", C.c_int64), ("envs_per_grid", C.c_int64), ("bits_t", C.c_void_p),
+                ("hier", C.c_void_p)]
 
 
 class RolloutArgs(C.Structure):
@@ -84,6 +85,10 @@ SYMBOLS = {
                            _vp, _vp, _i32, _vp, _u64, _i32, _i64, _i64, _i32, _vp]),
     "ag_rollout": (_i32, [C.POINTER(Params), C.POINTER(Grid), C.POINTER(RolloutArgs), _vp]),
     "ag_launch_count": (_i64, []),
+    "ag_grid_hier_bytes": (_i64, [_i32]),
+    "ag_grid_pack_hier": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp]),
+    "ag_cspace_map_words": (_i64, [C.POINTER(_i32), C.POINTER(_i32)]),
+    "ag_cspace_map": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp]),
     "ag_pipeline_create": (_i32, [C.POINTER(_vp), _i32, _i64, _i32, _i64, _i32, _i32, _i64]),
     "ag_pipeline_destroy": (None, [_vp]),
     "ag_rollout_host": (_i32, [_vp, C.POINTER(Params), C.POINTER(Grid), C.POINTER(RolloutArgs), _vp]),
@@ -110,7 +115,12 @@ def load():
                               "There is no CPU fallback." % (path, "stale" if os.path.exists(path) else "missing", e)) from e
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
-        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:   # an older build of the library: never run it
+            raise ImportError("abstract_gym_b200: %s does not export %s (include/abstract_gym_b200.h declares it): the "
+                              "library is older than the package; rebuild it with `python abstract_gym_b200/build.py "
+                              "--force`" % (path, name)) from e
         fn.restype, fn.argtypes = res, args
     if lib.ag_abi_version() != ABI_VERSION:
         raise ImportError("abstract_gym_b200: ABI version mismatch")

@@ -16,6 +16,7 @@ namespace agd {
 struct GridDev {
     const uint32_t *bits;
     const uint32_t *bits_t;   // transposed copy (lines = columns) or nullptr
+    const unsigned char *hier;   // two-level form (ag_grid.hier: 8x8 tiles + summary bitmap) or nullptr
     const double *min_x;
     const double *min_y;
     double side;       // E/(S-1)
@@ -28,6 +29,9 @@ struct GridDev {
     int32_t stage;     // 1: block-uniform grid, stage bits+tables into shared memory
     int64_t stride_words;
     int64_t envs_per_grid;
+    int32_t T, cwpr;          // hier: tiles per side, summary words per row
+    int32_t hier_tiles_bytes; // hier: bytes of the tile array (the summary bitmap follows it)
+    int32_t hier_bytes;       // hier: bytes per grid
 };
 
 // what one thread sees: either shared-memory copies or global pointers
@@ -36,7 +40,13 @@ struct GridView {
     const uint32_t *bits_t;   // nullptr when the grid has no transposed copy
     const double *min_x;
     const double *min_y;
+    const unsigned long long *tiles;   // two-level form: 8x8 tiles, T*T of them; nullptr = none
+    const uint32_t *coarse;            // ... and the T x T summary bitmap
 };
+__device__ __forceinline__ void view_hier(GridView &V, const GridDev &G, const unsigned char *h) {
+    V.tiles = reinterpret_cast<const unsigned long long *>(h);
+    V.coarse = h ? reinterpret_cast<const uint32_t *>(h + G.hier_tiles_bytes) : nullptr;
+}
 
 __device__ __forceinline__ int64_t grid_of_env(const GridDev &G, int64_t gid) {
     return G.n_grids == 1 ? 0 : (int64_t)(((uint64_t)gid / (uint64_t)G.envs_per_grid) % (uint64_t)G.n_grids);
@@ -310,20 +320,25 @@ __device__ __forceinline__ bool target_reached_at(const ag_params &P, double j1,
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // Stage this block's grid (bits + corner tables) into dynamic shared memory.  Layout:
-//   [mbarrier 16 B][bits: stride_words*4 B][bits_t: the same, if present][min_x: Spad*8][min_y: Spad*8]
+//   [mbarrier 16 B][bits: stride_words*4 B][bits_t: the same, if present][hier: hier_bytes, if present][min_x: Spad*8][min_y: Spad*8]
 __device__ __forceinline__ GridView stage_grid(const GridDev &G, int64_t block_gid0, unsigned char *smem) {
     GridView V;
     const int64_t g = grid_of_env(G, block_gid0);
     const uint32_t *gbits = G.bits + g * G.stride_words;
     const uint32_t *gbits_t = G.bits_t ? G.bits_t + g * G.stride_words : nullptr;
+    const unsigned char *ghier = G.hier ? G.hier + g * (int64_t)G.hier_bytes : nullptr;
     if (!G.stage) {
         V.bits = gbits; V.bits_t = gbits_t; V.min_x = G.min_x; V.min_y = G.min_y;
+        view_hier(V, G, ghier);
         return V;
     }
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     uint32_t *sbits = reinterpret_cast<uint32_t *>(smem + 16);
     const uint32_t bit_bytes = (uint32_t)G.stride_words * 4u;
-    const uint32_t all_bytes = G.bits_t ? 2u * bit_bytes : bit_bytes;
+    const uint32_t two_bytes = G.bits_t ? 2u * bit_bytes : bit_bytes;
+    const uint32_t hier_bytes = G.hier ? (uint32_t)G.hier_bytes : 0u;
+    const uint32_t all_bytes = two_bytes + hier_bytes;
+    unsigned char *shier = smem + 16 + two_bytes;
     const int spad = (G.S + 1) & ~1;
     double *sx = reinterpret_cast<double *>(smem + 16 + all_bytes);
     double *sy = sx + spad;
@@ -339,6 +354,9 @@ __device__ __forceinline__ GridView stage_grid(const GridDev &G, int64_t block_g
             if (gbits_t)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(smem_u32(sbits) + bit_bytes), "l"(gbits_t), "r"(bit_bytes), "r"(b) : "memory");
+            if (ghier)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(shier)), "l"(ghier), "r"(hier_bytes), "r"(b) : "memory");
         }
         __syncthreads();   // the barrier is initialised before anyone polls it
         const uint32_t b = smem_u32(mbar);
@@ -352,10 +370,13 @@ __device__ __forceinline__ GridView stage_grid(const GridDev &G, int64_t block_g
             sbits[i] = gbits[i];
             if (gbits_t) sbits[G.stride_words + i] = gbits_t[i];
         }
+        for (uint32_t i = threadIdx.x; i < hier_bytes / 4u; i += blockDim.x)
+            reinterpret_cast<uint32_t *>(shier)[i] = reinterpret_cast<const uint32_t *>(ghier)[i];
     }
     for (int i = threadIdx.x; i < G.S; i += blockDim.x) { sx[i] = G.min_x[i]; sy[i] = G.min_y[i]; }
     __syncthreads();
     V.bits = sbits; V.bits_t = G.bits_t ? sbits + G.stride_words : nullptr; V.min_x = sx; V.min_y = sy;
+    view_hier(V, G, G.hier ? shier : nullptr);
     return V;
 }
 

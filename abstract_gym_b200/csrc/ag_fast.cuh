@@ -388,6 +388,90 @@ __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, co
     return K.result;
 }
 
+// ---------------------------------------------------------------- two-level traversal (grids with ag_grid.hier)
+// The same conservative line walk as link_fast, but over the T x T summary bitmap (one bit per 8x8 tile): 8x fewer
+// lines and words, and only the cells of OCCUPIED tiles the link passes are examined -- each tile is one 64-bit word
+// whose set bits go to the narrow phase (narrow_f32's first test discards the cells the line misses in ~15
+// instructions).  Tile coordinates: fine column c = round(u) with u = x*inv_side + xoff covers u in [c-1/2, c+1/2), so
+// tile column C = c >> 3 covers (u + 1/2)/8 - 1/2 in [C-1/2, C+1/2); rows alike.
+__device__ __forceinline__ bool scan_tiles(const GridDev &G, const GridView &V, uint32_t word, int w, int line, LinkScan &K) {
+    while (word) {
+        const int tc = (w << 5) + __ffs(word) - 1;
+        word &= word - 1;
+        AG_CHECK_INDEX(line * G.T + tc, G.T * G.T);
+        unsigned long long tile = V.tiles[line * G.T + tc];
+        while (tile) {
+            const int b = __ffsll((long long)tile) - 1;
+            tile &= tile - 1;
+            if (!K.have_link) { K.L = make_link_f(K.p0x, K.p0y, K.p1x, K.p1y, K.side); K.have_link = true; }
+            const int r = (line << 3) + (b >> 3), c = (tc << 3) + (b & 7);
+            AG_CHECK_INDEX(r, G.S); AG_CHECK_INDEX(c, G.S);
+            const float mnx = (float)V.min_x[c], mny = (float)V.min_y[r];
+            const int v = narrow_f32(K.L, mnx, mny, mnx + K.side, mny + K.side);
+            if (v == 1) return true;
+            K.result |= v;          // 0 or 2
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool scan_tile_line(const GridDev &G, const GridView &V, const uint32_t *__restrict__ linep, int line,
+                                               int p_lo, int p_hi, LinkScan &K) {
+    const int w0 = p_lo >> 5, w1 = p_hi >> 5;
+    const uint32_t mlo = 0xFFFFFFFFu << (p_lo & 31), mhi = 0xFFFFFFFFu >> (31 - (p_hi & 31));
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t word = linep[w];
+        if (w == w0) word &= mlo;
+        if (w == w1) word &= mhi;
+        if (word != 0 && scan_tiles(G, V, word, w, line, K)) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ int link_fast_hier(const GridDev &G, const GridView &V, const FastConst &C, float p0x, float p0y,
+                                              float p1x, float p1y) {
+    // margin in tiles: the fine walk's margin (cells) / 8, plus slack for the float32 tile coordinates
+    const float mcell = (fmaxf(2.0e-6f * C.inv_side, 1.0e-3f) + 0.001f) * 0.125f + 0.001f;
+    const int T1 = G.T - 1;
+    const float inv8 = C.inv_side * 0.125f;
+    const float hi8 = C.half * inv8;
+    const float xoff = hi8 - 0.5f, roff = hi8 + (0.125f - 0.5f);          // ((xoff_fine + 1/2)/8 - 1/2), ((roff_fine + 1/2)/8 - 1/2)
+    const float pa = fmaf(p0x, inv8, xoff), pb = fmaf(p1x, inv8, xoff);    // tile columns of the end points
+    const float la = fmaf(-p0y, inv8, roff), lb = fmaf(-p1y, inv8, roff);  // tile rows of the end points
+    LinkScan K;
+    K.p0x = p0x; K.p0y = p0y; K.p1x = p1x; K.p1y = p1y; K.side = C.side; K.have_link = false; K.result = 0; K.swapped = false;
+    int l_lo = round_magic(fminf(la, lb) - mcell), l_hi = round_magic(fmaxf(la, lb) + mcell);
+    if (l_lo > T1 || l_hi < 0) return 0;
+    l_lo = max(l_lo, 0); l_hi = min(l_hi, T1);
+    const float pseg_lo = fminf(pa, pb), pseg_hi = fmaxf(pa, pb);
+    const uint32_t *linep = V.coarse + l_lo * G.cwpr;
+    const float dl = lb - la, dp = pb - pa;
+    const bool tracked = (l_hi - l_lo >= 2) && (fabsf(dl) * 64.0f >= fabsf(dp));
+    if (!tracked) {
+        const int p_lo = max(round_magic(pseg_lo - mcell), 0), p_hi = min(round_magic(pseg_hi + mcell), T1);
+        if (p_lo > p_hi) return 0;
+        for (int l = l_lo; l <= l_hi; ++l, linep += G.cwpr)
+            if (scan_tile_line(G, V, linep, l, p_lo, p_hi, K)) return 1;
+        return K.result;
+    }
+    // the position interval of tile row l follows the link: [p(l - 1/2), p(l + 1/2)] widened as in link_fast
+    const float s = dp * __frcp_rn(dl);
+    const float mm = mcell + 5.0e-5f * inv8 + fabsf(s) * mcell;
+    const float clamp_lo = pseg_lo - mm, clamp_hi = pseg_hi + mm;
+    const float pstart = fmaf(((float)l_lo - 0.5f) - la, s, pa);
+    float pprev = pstart, k = 1.0f;
+    for (int l = l_lo; l <= l_hi; ++l, linep += G.cwpr, k += 1.0f) {
+        const float pcur = fmaf(k, s, pstart);
+        const float lo = fmaxf(fminf(pprev, pcur) - mm, clamp_lo), hi = fminf(fmaxf(pprev, pcur) + mm, clamp_hi);
+        pprev = pcur;
+        const int p_lo = max(round_magic(lo), 0), p_hi = min(round_magic(hi), T1);
+        if (p_lo > p_hi) continue;
+        AG_CHECK_INDEX(l, G.T); AG_CHECK_INDEX(p_lo, G.T); AG_CHECK_INDEX(p_hi, G.T);
+        if (scan_tile_line(G, V, linep, l, p_lo, p_hi, K)) return 1;
+    }
+    return K.result;
+}
+
 // broad-phase selection: a compile-time choice for the rollout kernel (keeps its register
 // allocation small), a run-time one (BP_ANY) for K1..K3
 enum { BP_ANY = 0, BP_LIST = 1, BP_TRAVERSAL = 2 };
@@ -403,9 +487,10 @@ __device__ __forceinline__ int arm_fast(const GridDev &G, const GridView &V, con
     // link 2's row loop at 1.0 active thread per instruction (profiles/r1_c4_*).  Hence: no early return between
     // the links, and a __syncwarp over the lanes that entered together.
     const unsigned lanes = __activemask();
-    const int v1 = link_fast(G, V, C, 0.0f, 0.0f, a.ex, a.ey);
+    const bool hier = V.tiles != nullptr;                                   // uniform over the launch
+    const int v1 = hier ? link_fast_hier(G, V, C, 0.0f, 0.0f, a.ex, a.ey) : link_fast(G, V, C, 0.0f, 0.0f, a.ex, a.ey);
     __syncwarp(lanes);
-    const int v2 = (v1 == 1) ? 0 : link_fast(G, V, C, a.ex, a.ey, a.gx, a.gy);
+    const int v2 = (v1 == 1) ? 0 : (hier ? link_fast_hier(G, V, C, a.ex, a.ey, a.gx, a.gy) : link_fast(G, V, C, a.ex, a.ey, a.gx, a.gy));
     __syncwarp(lanes);
     return (v1 == 1 || v2 == 1) ? 1 : (v1 | v2);
 }

@@ -12,6 +12,8 @@ using namespace agd;
 // ag_rollout_lut.cu: the persistent kernel for scene_0-class grids (obstacle list, one grid, cartesian target)
 bool rollout_lut_applies(const ag_params &P, const GridDev &G, const RolloutDev &A);
 ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s);
+int64_t cspace_map_words(int32_t *b1, int32_t *b2);
+ag_status launch_cspace_map(const ag_params &P, const GridDev &G, uint32_t *map, cudaStream_t s);
 // ag_dense.cu: the warp-cooperative kernel for grids that go through the cell traversal (needs the transposed planes)
 bool rollout_coop_applies(const ag_params &P, const GridDev &G, const RolloutDev &A);
 ag_status launch_rollout_coop(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s);
@@ -37,6 +39,26 @@ __global__ void k_grid_pack(const uint8_t *__restrict__ occ, int S, int wpr, int
     const int c_end = min(S, (w + 1) * 32);
     for (int c = w * 32; c < c_end; ++c) word |= (row[c] != 0 ? 1u : 0u) << (c & 31);
     bits[g * stride_words + (int64_t)r * wpr + w] = word;
+}
+
+// bits -> the two-level form (ag_grid.hier): one thread per 8x8 tile; the summary bitmap is zeroed by the launcher
+__global__ void k_grid_pack_hier(const uint32_t *__restrict__ bits, int S, int wpr, int n_grids, int64_t stride_words,
+                                 unsigned char *__restrict__ hier, int T, int cwpr, int64_t tiles_bytes, int64_t hier_bytes) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)T * T * n_grids) return;
+    const int64_t g = i / ((int64_t)T * T);
+    const int R = (int)((i % ((int64_t)T * T)) / T), Cc = (int)(i % T);
+    const uint32_t *gb = bits + g * stride_words;
+    unsigned long long tile = 0;
+    for (int dr = 0; dr < 8; ++dr) {
+        const int r = R * 8 + dr;
+        if (r >= S) break;
+        const uint32_t byte = (gb[(int64_t)r * wpr + (Cc >> 2)] >> ((Cc & 3) * 8)) & 0xFFu;   // columns 8Cc .. 8Cc+7 of row r
+        tile |= (unsigned long long)byte << (dr * 8);
+    }
+    unsigned char *gh = hier + g * hier_bytes;
+    reinterpret_cast<unsigned long long *>(gh)[(int64_t)R * T + Cc] = tile;
+    if (tile) atomicOr(reinterpret_cast<uint32_t *>(gh + tiles_bytes) + R * cwpr + (Cc >> 5), 1u << (Cc & 31));
 }
 
 // ------------------------------------------------------------------------- predicate / FK arrays
@@ -695,14 +717,20 @@ ag_status make_grid_dev(const ag_params *p, const ag_grid *g, int64_t env_id0, i
         return AG_ERR_MODE;
     GridDev d;
     d.bits = g->bits; d.bits_t = g->bits_t; d.min_x = g->min_x; d.min_y = g->min_y;
+    d.hier = reinterpret_cast<const unsigned char *>(g->hier);
+    d.T = (g->S + 7) / 8; d.cwpr = (d.T + 31) / 32;
+    d.hier_tiles_bytes = (int32_t)((((int64_t)d.T * d.T + 1) & ~(int64_t)1) * 8);
+    d.hier_bytes = (int32_t)ag_grid_hier_bytes(g->S);
     d.side = g->side; d.half = g->env_size / 2.0; d.inv_side = 1.0 / g->side;
     d.margin = 1e-9 * g->env_size;
     d.S = g->S; d.wpr = g->words_per_row; d.n_grids = g->n_grids;
     d.stride_words = g->grid_stride_words; d.envs_per_grid = g->envs_per_grid;
     const int spad = (g->S + 1) & ~1;
-    const size_t bytes = 16 + (size_t)g->grid_stride_words * 4 * (g->bits_t ? 2 : 1) + (size_t)spad * 16;
+    const size_t bytes = 16 + (size_t)g->grid_stride_words * 4 * (g->bits_t ? 2 : 1) + (g->hier ? (size_t)d.hier_bytes : 0) +
+                         (size_t)spad * 16;
     const bool uniform = g->n_grids == 1 || (g->envs_per_grid % AG_BLOCK == 0 && env_id0 % AG_BLOCK == 0);
-    const bool aligned = ((uintptr_t)g->bits % 16 == 0) && ((uintptr_t)g->bits_t % 16 == 0) && (g->grid_stride_words % 4 == 0);
+    const bool aligned = ((uintptr_t)g->bits % 16 == 0) && ((uintptr_t)g->bits_t % 16 == 0) && ((uintptr_t)g->hier % 16 == 0) &&
+                         (g->grid_stride_words % 4 == 0);
     d.stage = (uniform && aligned && bytes <= (size_t)stage_max_bytes()) ? 1 : 0;
     *smem_bytes = d.stage ? bytes : 0;
     *out = d;
@@ -855,6 +883,21 @@ ag_status ag_grid_pack(const uint8_t *occ, int32_t S, int32_t n_grids, uint32_t 
     return launched();
 }
 
+ag_status ag_grid_pack_hier(const uint32_t *bits, int32_t S, int32_t n_grids, int64_t grid_stride_words, void *hier,
+                            void *stream) {
+    if (!bits || !hier) return AG_ERR_NULL;
+    const int wpr = (S + 31) / 32;
+    if (S < 2 || n_grids < 1 || grid_stride_words < (int64_t)S * wpr) return AG_ERR_SHAPE;
+    if ((uintptr_t)hier % 16) return AG_ERR_ALIGN;
+    const int T = (S + 7) / 8, cwpr = (T + 31) / 32;
+    const int64_t hb = ag_grid_hier_bytes(S), tb = (((int64_t)T * T + 1) & ~(int64_t)1) * 8;
+    cudaError_t e = cudaMemsetAsync(hier, 0, (size_t)hb * n_grids, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (ag_status)e;
+    k_grid_pack_hier<<<blocks_for((int64_t)T * T * n_grids), AG_BLOCK, 0, (cudaStream_t)stream>>>(
+        bits, S, wpr, n_grids, grid_stride_words, reinterpret_cast<unsigned char *>(hier), T, cwpr, tb, hb);
+    return launched();
+}
+
 ag_status ag_segment_square(const double *seg, const double *sq, double section_eps, uint8_t *hit, double *abc,
                             double *corner_values, int64_t *axis_aligned, int64_t n, void *stream) {
     if (n < 0) return AG_ERR_SHAPE;
@@ -992,6 +1035,19 @@ ag_status ag_step_obs(const ag_params *p, const ag_grid *g, double *j1, double *
     AG_DISPATCH_ENGINE(engine, { if (actions_f32) AG_SO(true) else AG_SO(false) });
 #undef AG_SO
     return launched();
+}
+
+int64_t ag_cspace_map_words(int32_t *b1, int32_t *b2) { return cspace_map_words(b1, b2); }
+
+ag_status ag_cspace_map(const ag_params *p, const ag_grid *g, uint32_t *map, void *stream) {
+    if (!p || !g || !map) return AG_ERR_NULL;
+    if (g->n_grids != 1 || g->S > 32) return AG_ERR_SHAPE;
+    if ((uintptr_t)map % 16) return AG_ERR_ALIGN;
+    GridDev G;
+    size_t smem;
+    ag_status st = make_grid_dev(p, g, 0, AG_ENGINE_FAST, &G, &smem);
+    if (st) return st;
+    return launch_cspace_map(*p, G, map, (cudaStream_t)stream);
 }
 
 ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream) {

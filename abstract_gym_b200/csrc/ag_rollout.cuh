@@ -67,10 +67,11 @@ __device__ __forceinline__ BlockCtx block_prologue(const GridDev &G, int64_t env
             B.fl = s_fl;
         }
     } else {
-        const int64_t off = grid_of_env(G, env_id0 + min(e, n - 1)) * G.stride_words;
+        const int64_t gi = grid_of_env(G, env_id0 + min(e, n - 1)), off = gi * G.stride_words;
         B.V.bits = G.bits + off;
         B.V.bits_t = G.bits_t ? G.bits_t + off : nullptr;
         B.V.min_x = G.min_x; B.V.min_y = G.min_y;
+        view_hier(B.V, G, G.hier ? G.hier + gi * (int64_t)G.hier_bytes : nullptr);
     }
     return B;
 }
@@ -144,13 +145,16 @@ __device__ __forceinline__ GridView thread_view(const GridDev &G, unsigned char 
         const uint32_t bit_bytes = (uint32_t)G.stride_words * 4u;
         V.bits = reinterpret_cast<const uint32_t *>(smem + 16);
         V.bits_t = G.bits_t ? V.bits + G.stride_words : nullptr;
-        V.min_x = reinterpret_cast<const double *>(smem + 16 + (G.bits_t ? 2u * bit_bytes : bit_bytes));
+        const uint32_t two_bytes = G.bits_t ? 2u * bit_bytes : bit_bytes;
+        view_hier(V, G, G.hier ? smem + 16 + two_bytes : nullptr);
+        V.min_x = reinterpret_cast<const double *>(smem + 16 + two_bytes + (G.hier ? (uint32_t)G.hier_bytes : 0u));
         V.min_y = V.min_x + spad;
     } else {
-        const int64_t off = grid_of_env(G, gid) * G.stride_words;
+        const int64_t gi = grid_of_env(G, gid), off = gi * G.stride_words;
         V.bits = G.bits + off;
         V.bits_t = G.bits_t ? G.bits_t + off : nullptr;
         V.min_x = G.min_x; V.min_y = G.min_y;
+        view_hier(V, G, G.hier ? G.hier + gi * (int64_t)G.hier_bytes : nullptr);
     }
     return V;
 }

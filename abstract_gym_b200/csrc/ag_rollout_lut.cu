@@ -32,6 +32,8 @@
 //   record (2 F2F + 2 STG) -> vote.
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 
 #include "ag_rollout.cuh"
 
@@ -51,6 +53,24 @@ namespace {
 #define AG_LUT_BLOCKS_PER_SM 2
 #endif
 
+// configuration-space map (CMAP form of the kernel): 2^CB1 x 2^CB2 bins over (joint_1, joint_2) mod 2pi, one bit each
+#ifndef AG_CMAP_B1
+#define AG_CMAP_B1 10
+#endif
+#ifndef AG_CMAP_B2
+#define AG_CMAP_B2 8
+#endif
+constexpr int CB1 = AG_CMAP_B1, CB2 = AG_CMAP_B2;
+static_assert(CB1 >= 6 && CB2 >= 6 && CB1 + CB2 <= 20, "the map must fit shared memory");
+constexpr int CMAP_WORDS = 1 << (CB1 + CB2 - 5);
+constexpr int CMAP_HDR_WORDS = 64;                       // 256-byte header in front of the map words
+constexpr int CMAP_SLOTS = 16;
+struct CmapHeader {
+    unsigned long long key;                              // hash of everything the map depends on; 0 = never built
+    unsigned int done[CMAP_SLOTS];                       // blocks finished, one counter per in-flight build
+};
+static_assert(sizeof(CmapHeader) <= CMAP_HDR_WORDS * 4, "header");
+
 constexpr int B1 = AG_LUT_B1, B2 = AG_LUT_B2;            // bins: 2^B1 for link 1 (also the resolution of its hazard bit), 2^B2 for link 2
 constexpr int N1 = 1 << B1, N2 = 1 << B2;
 static_assert(B1 >= 9 && B2 >= 9 && B1 <= 11 && B2 <= 11, "sub-bin phase must fit 23 bits; tables must fit static shared memory");
@@ -59,7 +79,12 @@ constexpr int LB = 256, LW = LB / 32;
 // ahead of their use; slot (t mod RING) of the warp's ring holds row t.  (Register prefetch does not work here: ptxas
 // gives all in-flight LDGs of the loop ONE scoreboard slot, so a consumer waits for every outstanding load and the
 // effective distance is a single step: profiles/r2b.)
-constexpr int RING = 4;
+#ifndef AG_LUT_RING
+#define AG_LUT_RING 4
+#endif
+constexpr int RING = AG_LUT_RING;
+static_assert((RING & (RING - 1)) == 0 && RING >= 4, "ring slots: a power of two");
+
 constexpr double PHASE_MAGIC = 6755399441055744.0;       // 1.5 * 2^52: the add rounds to an integer in the low word
 constexpr double TWO_PI = 6.283185307179586476925;
 constexpr float RAD_PER_UNIT = (float)(TWO_PI / 4294967296.0);   // one phase unit (2^-32 turn) in radians
@@ -73,6 +98,8 @@ struct LutConst {
     int64_t n_tiles;
     uint32_t ss_off;        // byte offset of SlowShared in dynamic shared memory (after the staged grid)
     uint32_t slot;          // this launch's pair of tile / done counters (g_tile_sched)
+    uint32_t cmap_off;      // CMAP: byte offset of the map's shared-memory copy in the dynamic segment
+    const uint32_t *cmap;   // CMAP: the map words in global memory (k_cspace_build)
 };
 
 // Dynamic tile scheduling: warps draw 32-env tiles from a device-global counter, so no warp idles while tiles remain
@@ -98,7 +125,14 @@ struct SlowShared {
     int t[LB];
     int cr[LB];                // level 1's verdicts for level 2: 0 = no event, else 16 | c | r << 2
     uint32_t sc0[LB];          // action draw counter at the start of the launch (Philox actions)
+    // Episode statistics of the current tile, one private cell per lane (no atomics: 64-bit shared atomics are
+    // compare-and-swap loops, five of them per episode end cost 3 % of the kernel -- profiles/r2); the warp folds
+    // them into its own row of s_wacc when the tile ends.
+    unsigned long long len_sum[LB];
+    uint32_t n_ep[LB], n_col[LB], n_suc[LB], n_cold[LB], n_exact[LB];
+    int ret[LB];
 };
+enum { WA_EPISODES = 0, WA_COLLISIONS, WA_SUCCESSES, WA_LEN_SUM, WA_RETURN, WA_ENV_STEPS, WA_COLD, WA_EXACT, WA_EXITS, WA_COUNT };
 
 __device__ __forceinline__ void add64(unsigned long long *s_acc, int slot, long long v) {
     atomicAdd(&s_acc[slot], (unsigned long long)v);
@@ -166,7 +200,7 @@ __device__ __forceinline__ void settle_step(const ag_params &P, const GridDev &G
         const GridView V = thread_view(G, const_cast<unsigned char *>(smem_grid), A.env_id0 + e);
         d = cold_exact_decide_at(P, G, V, fl, q1, q2, c, r, txd, tyd);
         cold = true;
-        if (A.diag != nullptr) add64(s_acc, AG_ST_COUNT + AG_DIAG_EXACT_STEPS, 1);
+        ss.n_exact[x] += 1;
     }
     float rw = ss.rw[x];
     uint32_t f = ss.fl[x];
@@ -181,11 +215,11 @@ __device__ __forceinline__ void settle_step(const ag_params &P, const GridDev &G
     emit_event(A, e, t, rw, f);
     if (f) {                                                                     // experiment_0.py:30-34
         cold = true;
-        add64(s_acc, AG_ST_EPISODES, 1);
-        if (f & AG_FLAG_COLLISION) add64(s_acc, AG_ST_COLLISIONS, 1);
-        if (f & AG_FLAG_DONE) add64(s_acc, AG_ST_SUCCESSES, 1);
-        add64(s_acc, AG_ST_EP_LEN_SUM, (long long)ss.el_off[x] + t + 1);
-        add64(s_acc, AG_ST_RETURN_MILLI, (long long)__float2int_rn(rw * 1e-3f));
+        ss.n_ep[x] += 1;
+        if (f & AG_FLAG_COLLISION) ss.n_col[x] += 1;
+        if (f & AG_FLAG_DONE) ss.n_suc[x] += 1;
+        ss.len_sum[x] += (unsigned long long)((long long)ss.el_off[x] + t + 1);
+        ss.ret[x] += __float2int_rn(rw * 1e-3f);
         if (d & 1) {   // Scene.reset(): the pose is unchanged since the step, so collision_check() == (d & 1)
             uint32_t info = ss.cinfo[x];
             if (info & PD_VALID) {
@@ -205,7 +239,7 @@ __device__ __forceinline__ void settle_step(const ag_params &P, const GridDev &G
         }
         rw = 0.0f; f = 0; ss.el_off[x] = -(t + 1);                               // scene_0.py:111-113
     }
-    if (cold && A.diag != nullptr) add64(s_acc, AG_ST_COUNT + AG_DIAG_COLD_CALLS, 1);
+    if (cold) ss.n_cold[x] += 1;
     ss.rw[x] = rw; ss.fl[x] = f;
     ss.q1[x] = q1; ss.q2[x] = q2;
     ss.thr[x] = (f != 0 || rw != 0.0f) ? __int_as_float(0x7f800000) : thr_clean;
@@ -229,8 +263,12 @@ __device__ __forceinline__ float2 taylor_turn(float2 t, float d) {
 // unless the origin lies inside the inflated square, does not contain the origin, so its extent is spanned by its
 // vertices: corners inside the disc and circle / edge crossings (a ray from the centre is never tangent to the circle).
 // half < 0: never; half >= pi: always.
+__device__ void hazard_interval(double X0, double Y0, double X1, double Y1, double l1, float &mid, float &half);
 __device__ void hazard_interval(float4 sq, double l1, double mg, float &mid, float &half) {
-    const double X0 = (double)sq.x - mg, Y0 = (double)sq.y - mg, X1 = (double)sq.z + mg, Y1 = (double)sq.w + mg;
+    hazard_interval((double)sq.x - mg, (double)sq.y - mg, (double)sq.z + mg, (double)sq.w + mg, l1, mid, half);
+}
+// the same for an (already inflated) box X0..X1 x Y0..Y1
+__device__ void hazard_interval(double X0, double Y0, double X1, double Y1, double l1, float &mid, float &half) {
     if (X0 <= 0.0 && X1 >= 0.0 && Y0 <= 0.0 && Y1 >= 0.0) { mid = 0.0f; half = 4.0f; return; }
     const double r2 = l1 * l1;
     const double ref = atan2(0.5 * (Y0 + Y1), 0.5 * (X0 + X1));
@@ -292,6 +330,171 @@ __device__ void fill_table(float2 *lut, int n, double len, const float *hz, int 
     }
 }
 
+// ------------------------------------------------------------------------- configuration-space map (CMAP)
+// One bit per bin of (joint_1, joint_2) mod 2pi: CLEAR = for every pose of the bin both links stay farther than CMAP_MG
+// from every occupied square and the end effector stays outside the target box (scene_0.py:129-130) by more than
+// CMAP_MG, i.e. the step is certainly uneventful and the hot loop needs no forward kinematics at all -- two DFMA for
+// the phases, one shared-memory word, one bit test.  SET = "look closer": the lane takes the slow path, which decides
+// exactly as before.  So the map only has to be CONSERVATIVE; it is built from lower bounds of distances:
+//   * over a bin, joint_1 in [a1-d1, a1+d1] and joint_2 in [a2-d2, a2+d2], the elbow stays within the sagitta
+//     l1(1-cos d1) of the chord Ea..Eb and link 2's direction vector within l2(1-cos d2) of the triangle 0, Ua, Ub, so
+//     link 2 sweeps a subset of the convex polygon hull({Ea,Eb} + {0,Ua,Ub}) inflated by the two sagittas;
+//   * the distance from that polygon to a square is bounded from below by the largest separation along a finite set
+//     of unit axes (every axis gives a valid lower bound; the set -- box normals, the link normals at the bin's centre
+//     and edges, the chord normal, and the directions from the square's corners to the centre pose's elbow and end
+//     effector -- makes the bound tight for edge/vertex and vertex/vertex contacts);
+//   * link 1 depends on joint_1 only and uses the exact angular intervals of hazard_interval().
+// 2.0e-6 m covers the rounding of the phase (< 1e-9 rad), of this float64 construction, and the reference's own
+// rounding noise (< 1e-12 m): the same margin the float32 broad phase uses.
+// The map depends on the grid, the link lengths, the target and its tolerance.  It lives in a library-owned device
+// buffer that is reused between launches: every launch re-derives a 64-bit key from the CURRENT grid words and
+// parameters on the device (thread 0 of each block, ~100 words) and rebuilds the map only when the stored key differs.
+constexpr double CMAP_MG = 2.0e-6;
+constexpr int CMAP_BUILD_BLOCKS = 128;
+constexpr uint32_t CMAP_VERSION = 1;
+
+struct V2 { double x, y; };
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long v) {
+    h ^= v;
+    h *= 0x100000001B3ull;                                                       // FNV-1a over 64-bit words
+    return h ^ (h >> 29);
+}
+
+// separation of the point set P and the box (centre c, half extents hx, hy) along the unit axis n (negative: overlap)
+template <int NP>
+__device__ __forceinline__ double axis_gap(V2 n, const V2 (&P)[NP], V2 c, double hx, double hy) {
+    double lo = 1.0e300, hi = -1.0e300;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const double d = n.x * P[i].x + n.y * P[i].y;
+        lo = fmin(lo, d); hi = fmax(hi, d);
+    }
+    const double cc = n.x * c.x + n.y * c.y, r = fabs(n.x) * hx + fabs(n.y) * hy;
+    return fmax(lo - (cc + r), (cc - r) - hi);
+}
+
+__global__ void __launch_bounds__(256)
+k_cspace_build(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G, uint32_t *buf, uint32_t slot) {
+    __shared__ unsigned long long s_key;
+    __shared__ int s_skip, s_m;
+    __shared__ double s_sq[AG_LIST_MAX][4];
+    __shared__ float s_hz[2 * AG_LIST_MAX];
+    CmapHeader *H = reinterpret_cast<CmapHeader *>(buf);
+    if (threadIdx.x == 0) {
+        unsigned long long h = 0xCBF29CE484222325ull;
+        h = mix64(h, ((unsigned long long)CMAP_VERSION << 48) | ((unsigned long long)CB1 << 40) | ((unsigned long long)CB2 << 32) | (unsigned)G.S);
+        const double par[6] = {P.link_1, P.link_2, P.target_x, P.target_y, P.reach_eps, G.side};
+        for (int i = 0; i < 6; ++i) h = mix64(h, (unsigned long long)__double_as_longlong(par[i]));
+        int m = 0;
+        for (int r = 0; r < G.S; ++r) {
+            h = mix64(h, (unsigned long long)__double_as_longlong(G.min_y[r]));
+            h = mix64(h, (unsigned long long)__double_as_longlong(G.min_x[r]));
+            for (int w = 0; w < G.wpr; ++w) {
+                uint32_t word = G.bits[r * G.wpr + w];
+                h = mix64(h, word);
+                while (word) {
+                    const int c = (w << 5) + __ffs(word) - 1;
+                    word &= word - 1;
+                    if (m < AG_LIST_MAX && c < G.S) {
+                        const double mnx = G.min_x[c], mny = G.min_y[r];
+                        s_sq[m][0] = mnx; s_sq[m][1] = mny;
+                        s_sq[m][2] = __dadd_rn(mnx, G.side); s_sq[m][3] = __dadd_rn(mny, G.side);   // occupancy_grid.py:66-67
+                    }
+                    ++m;
+                }
+            }
+        }
+        h |= 1ull;                                                               // 0 means "never built"
+        s_key = h;
+        s_m = m > AG_LIST_MAX ? -1 : m;                                          // no obstacle list: every bin is slow
+        s_skip = (*reinterpret_cast<volatile unsigned long long *>(&H->key) == h) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_skip) {
+        const int m = s_m;
+        if ((int)threadIdx.x < m)
+            hazard_interval(s_sq[threadIdx.x][0] - CMAP_MG, s_sq[threadIdx.x][1] - CMAP_MG, s_sq[threadIdx.x][2] + CMAP_MG,
+                            s_sq[threadIdx.x][3] + CMAP_MG, P.link_1, s_hz[2 * threadIdx.x], s_hz[2 * threadIdx.x + 1]);
+        __syncthreads();
+        constexpr int N1c = 1 << CB1, N2c = 1 << CB2;
+        const double l1 = P.link_1, l2 = P.link_2;
+        double sd, cd;
+        sincospi(1.0 / (double)N1c, &sd, &cd);
+        const double sag1 = l1 * (1.0 - cd);
+        sincospi(1.0 / (double)N2c, &sd, &cd);
+        const double sag2 = l2 * (1.0 - cd);
+        const double infl = sag1 + sag2 + CMAP_MG;
+        const float hw1 = (float)(TWO_PI / (double)(2 * N1c)) + 2.0e-6f;          // half a bin of joint_1 + rounding
+        for (int bin = blockIdx.x * 256 + threadIdx.x; bin < N1c * N2c; bin += gridDim.x * 256) {   // a warp = 32 bins of joint_2
+            const int b1 = bin >> CB2, b2 = bin & (N2c - 1);
+            bool haz = m < 0;
+            // ---- link 1: exact angular intervals
+            const float th1 = ((float)b1 + 0.5f) * (float)(TWO_PI / (double)N1c);
+            for (int k = 0; k < m; ++k) {
+                float dlt = th1 - s_hz[2 * k];
+                dlt -= (float)TWO_PI * rintf(dlt * (float)(1.0 / TWO_PI));
+                if (fabsf(dlt) <= s_hz[2 * k + 1] + hw1) haz = true;
+            }
+            // ---- link 2: the swept polygon against every square
+            V2 Ea, Eb, Ec, Ua, Ub, Uc;
+            sincospi(2.0 * (double)b1 / (double)N1c, &Ea.y, &Ea.x);
+            sincospi(2.0 * (double)(b1 + 1) / (double)N1c, &Eb.y, &Eb.x);
+            sincospi((2.0 * (double)b1 + 1.0) / (double)N1c, &Ec.y, &Ec.x);
+            sincospi(2.0 * (double)b2 / (double)N2c, &Ua.y, &Ua.x);
+            sincospi(2.0 * (double)(b2 + 1) / (double)N2c, &Ub.y, &Ub.x);
+            sincospi((2.0 * (double)b2 + 1.0) / (double)N2c, &Uc.y, &Uc.x);
+            const V2 n1c = {Ec.x, Ec.y};                                          // normal of the elbow chord = link 1's direction
+            const V2 n2a = {-Ua.y, Ua.x}, n2b = {-Ub.y, Ub.x}, n2c = {-Uc.y, Uc.x};   // link 2's normals at the bin's edges / centre
+            const V2 ea = {l1 * Ea.x, l1 * Ea.y}, eb = {l1 * Eb.x, l1 * Eb.y}, ec = {l1 * Ec.x, l1 * Ec.y};
+            const V2 ua = {l2 * Ua.x, l2 * Ua.y}, ub = {l2 * Ub.x, l2 * Ub.y};
+            const V2 gc = {ec.x + l2 * Uc.x, ec.y + l2 * Uc.y};
+            const V2 poly[6] = {ea, eb, {ea.x + ua.x, ea.y + ua.y}, {ea.x + ub.x, ea.y + ub.y},
+                                {eb.x + ua.x, eb.y + ua.y}, {eb.x + ub.x, eb.y + ub.y}};
+            for (int k = 0; k < m && !haz; ++k) {
+                const V2 c = {0.5 * (s_sq[k][0] + s_sq[k][2]), 0.5 * (s_sq[k][1] + s_sq[k][3])};
+                const double hx = 0.5 * (s_sq[k][2] - s_sq[k][0]), hy = 0.5 * (s_sq[k][3] - s_sq[k][1]);
+                double gap = axis_gap(V2{1.0, 0.0}, poly, c, hx, hy);
+                gap = fmax(gap, axis_gap(V2{0.0, 1.0}, poly, c, hx, hy));
+                gap = fmax(gap, axis_gap(n2c, poly, c, hx, hy));
+                gap = fmax(gap, axis_gap(n2a, poly, c, hx, hy));
+                gap = fmax(gap, axis_gap(n2b, poly, c, hx, hy));
+                gap = fmax(gap, axis_gap(n1c, poly, c, hx, hy));
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) {                                     // corner -> centre pose's end effector / elbow
+                    const double qx = (j & 1) ? s_sq[k][2] : s_sq[k][0], qy = (j & 2) ? s_sq[k][3] : s_sq[k][1];
+                    const V2 from = (j & 4) ? ec : gc;
+                    const double vx = from.x - qx, vy = from.y - qy, nv = sqrt(vx * vx + vy * vy);
+                    if (nv > 1.0e-9) gap = fmax(gap, axis_gap(V2{vx / nv, vy / nv}, poly, c, hx, hy) * (1.0 - 1.0e-12));
+                }
+                if (!(gap > infl)) haz = true;
+            }
+            // ---- the target box (scene_0.py:129-130) against the box of the swept end effector
+            {
+                const double gx0 = fmin(fmin(poly[2].x, poly[3].x), fmin(poly[4].x, poly[5].x)) - infl;
+                const double gx1 = fmax(fmax(poly[2].x, poly[3].x), fmax(poly[4].x, poly[5].x)) + infl;
+                const double gy0 = fmin(fmin(poly[2].y, poly[3].y), fmin(poly[4].y, poly[5].y)) - infl;
+                const double gy1 = fmax(fmax(poly[2].y, poly[3].y), fmax(poly[4].y, poly[5].y)) + infl;
+                const double e = fabs(P.reach_eps);
+                if (!(gx0 > P.target_x + e || gx1 < P.target_x - e || gy0 > P.target_y + e || gy1 < P.target_y - e)) haz = true;
+            }
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, haz);
+            if ((threadIdx.x & 31) == 0) buf[CMAP_HDR_WORDS + (bin >> 5)] = word;
+        }
+    }
+    // the last block of this launch publishes the key (blocks that skipped count too: the map they saw was complete)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&H->done[slot], 1u) == gridDim.x - 1) {
+            H->done[slot] = 0;
+            *reinterpret_cast<volatile unsigned long long *>(&H->key) = s_key;
+            __threadfence();
+        }
+    }
+}
+
+
 // The float32 arm from the tables (see the header of this file): elbow, half of link 2, link 1's hazard bit.
 struct TableArm { float2 ev, hv; uint32_t hazard; };
 __device__ __forceinline__ TableArm table_arm(double q1, double q2, double phase_scale, uint32_t lut1_a, uint32_t lut2_a) {
@@ -308,29 +511,41 @@ __device__ __forceinline__ TableArm table_arm(double q1, double q2, double phase
     return a;
 }
 
-template <bool HAS_ACT, bool RECORD, bool M3>
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// CMAP = true: the hot loop consults the configuration-space map instead of computing the table arm (scene-wide target only)
+template <bool HAS_ACT, bool RECORD, bool M3, bool CMAP>
 __global__ void __launch_bounds__(LB, AG_LUT_BLOCKS_PER_SM)
 k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G, const __grid_constant__ FastConst C,
               const __grid_constant__ RolloutDev A, const __grid_constant__ LutConst L) {
     extern __shared__ __align__(16) unsigned char smem_grid[];  // the staged grid (layout of stage_grid), then SlowShared
-    __shared__ __align__(16) float2 s_lut1[N1], s_lut2[N2];
+    __shared__ __align__(16) float2 s_lut1[CMAP ? 1 : N1], s_lut2[CMAP ? 1 : N2];
     __shared__ __align__(16) float2 s_ring[LW][RING][32];   // action rows t .. t+3 of each warp's tile (cp.async)
     __shared__ FastList s_fl;
     __shared__ float s_hz[2 * AG_LIST_MAX];
     __shared__ unsigned long long s_acc[AG_ST_COUNT + AG_DIAG_COUNT];
+    __shared__ long long s_wacc[LW][WA_COUNT];                  // per-warp totals over its tiles (lane 0 owns the row)
     __shared__ unsigned int s_done;
     __shared__ int64_t s_tile[LW];                              // each warp's current tile
     __shared__ int s_exits[LW];                                 // diagnostics: exits of the hot loop, per warp
     SlowShared &ss = *reinterpret_cast<SlowShared *>(smem_grid + L.ss_off);     // dynamic: static shared memory is capped at 48 KB
     if (threadIdx.x < AG_ST_COUNT + AG_DIAG_COUNT) s_acc[threadIdx.x] = 0;
+    if (threadIdx.x < LW * WA_COUNT) (&s_wacc[0][0])[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_done = 0;
     if (threadIdx.x < LW) s_exits[threadIdx.x] = 0;
     {
         const GridView V = stage_grid(G, A.env_id0, smem_grid);                  // one grid: block-uniform
         build_fast_list(G, V, &s_fl);
     }
-    // ---- the two tables
-    {
+    if constexpr (CMAP) {                                                        // ---- the map: global -> shared
+        const uint4 *src = reinterpret_cast<const uint4 *>(L.cmap);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem_grid + L.cmap_off);
+        for (int i = threadIdx.x; i < CMAP_WORDS / 4; i += LB) dst[i] = src[i];
+    } else {                                                                     // ---- the two tables
         const int m = s_fl.m;
         if ((int)threadIdx.x < m) hazard_interval(s_fl.sq[threadIdx.x], P.link_1, 2.0e-6, s_hz[2 * threadIdx.x], s_hz[2 * threadIdx.x + 1]);
         __syncthreads();
@@ -373,6 +588,7 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
             // episode end clears it: an infinite threshold makes its reach pre-test fire
             ss.thr[x] = (fl0 != 0 || rw0 != 0.0f) ? INF : L.thr_c;
             ss.t[x] = 0;
+            ss.len_sum[x] = 0; ss.n_ep[x] = 0; ss.n_col[x] = 0; ss.n_suc[x] = 0; ss.n_cold[x] = 0; ss.n_exact[x] = 0; ss.ret[x] = 0;
             if (HAS_ACT) {                                                       // rows 0 .. RING-2 in flight
                 const uint32_t ring_lane = smem_u32(&s_ring[x >> 5][0][lane]);
                 const float2 *ap = reinterpret_cast<const float2 *>(A.actions) + e;
@@ -411,6 +627,8 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
         asm volatile("mov.u32 %0, %1;" : "=r"(lut1_a) : "r"(smem_u32(s_lut1)));
         asm volatile("mov.u32 %0, %1;" : "=r"(lut2_a) : "r"(smem_u32(s_lut2)));
         asm volatile("mov.u32 %0, %1;" : "=r"(ring_lane) : "r"(smem_u32(&s_ring[x >> 5][0][lane])));
+        uint32_t cmap_a;
+        asm volatile("mov.u32 %0, %1;" : "=r"(cmap_a) : "r"(smem_u32(smem_grid + L.cmap_off)));
         int64_t sa = A.row_stride * (int64_t)sizeof(float2), sr = A.row_stride * (int64_t)sizeof(float);
         asm volatile("" : "+l"(sa));
         asm volatile("" : "+l"(sr));
@@ -447,6 +665,20 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
             }
             q1 = __dadd_rn(q1, d1); q2 = __dadd_rn(q2, d2);                      // two_joint_robot.py:71-72
             const bool inr = (fabs(q1) < 1048576.0) && (fabs(q2) < 1048576.0);   // NaN-safe: NaN is slow
+            if constexpr (CMAP) {
+                const uint32_t x1 = (uint32_t)__double2loint(fma(q1, L.phase_scale, PHASE_MAGIC));
+                const uint32_t x2 = (uint32_t)__double2loint(fma(q2, L.phase_scale, PHASE_MAGIC));
+                const uint32_t bit = ((x1 >> (32 - CB1)) << CB2) | (x2 >> (32 - CB2));
+                const uint32_t w = lds_u32(cmap_a + ((bit >> 3) & ~3u));
+                l_inr = inr;
+                if (RECORD) {
+                    __stcs(reinterpret_cast<float *>(p1), (float)q1);
+                    __stcs(reinterpret_cast<float *>(p2), (float)q2);
+                    p1 += sr; p2 += sr;
+                }
+                // a set bit, sticky state (thr == INF), or an angle outside the phase's range (also NaN)
+                return (((w >> (bit & 31u)) & 1u) != 0) || !(thr < INF) || !inr;
+            }
             const TableArm ta = table_arm(q1, q2, L.phase_scale, lut1_a, lut2_a);
             const float2 ev = ta.ev, hv = ta.hv;
             const float c2x = ev.x + hv.x, c2y = ev.y + hv.y;                    // centre of link 2's box; half extents |hv|
@@ -479,8 +711,8 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
             // masked on the rare path.
             return (ta.hazard != 0) || !(sep >= hm) || !(worst >= thr) || !inr;
         };
-        // Ring slot of step t: ring_lane + (t mod RING) * 256.  Invariant at the top of the loop: rows t .. t+2 are in
-        // flight or landed in their slots, pa points at row t+3.
+        // Ring slot of step t: ring_lane + (t mod RING) * 256.  Invariant at the top of the loop: rows t .. t+RING-2 are
+        // in flight or landed in their slots, pa points at row t+RING-1.
         auto issue_row = [&](int row) {                                          // row `row` -> its slot, if it exists
             if (HAS_ACT) {
                 if (row < K && active) cp_async8(ring_lane + (((uint32_t)row & (RING - 1)) << 8), pa);
@@ -513,7 +745,14 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
             event = false;
             if (slow && active) {
                 int c = 2, r = 2;
-                if (l_inr) {
+                if (CMAP) {                                                      // the hot loop had no arm: float32 FK now
+                    bool ok;
+                    const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
+                    if (ok) {
+                        c = s_fl.m < 0 ? 2 : arm_fast_list(&s_fl, a, C, true);
+                        r = reach_fast_at(C, a, tx, ty);
+                    }
+                } else if (l_inr) {
                     ArmF a;
                     a.ex = l_ex; a.ey = l_ey; a.gx = l_gx; a.gy = l_gy;
                     if (s_fl.m < 0) {
@@ -548,9 +787,25 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
                 A.reset_ctr[e] = ss.rc[x];
             }
             const int n_act = __popc(__ballot_sync(0xFFFFFFFFu, active));
+            // fold the tile's per-lane counters into the warp's row
+            const uint32_t ne = __reduce_add_sync(0xFFFFFFFFu, ss.n_ep[x]);
+            const uint32_t ncold = __reduce_add_sync(0xFFFFFFFFu, ss.n_cold[x]);
+            long long *wa = s_wacc[x >> 5];
+            if (ne != 0 || ncold != 0) {                                         // warp-uniform
+                const uint32_t nc = __reduce_add_sync(0xFFFFFFFFu, ss.n_col[x]), ns = __reduce_add_sync(0xFFFFFFFFu, ss.n_suc[x]);
+                const uint32_t nx = __reduce_add_sync(0xFFFFFFFFu, ss.n_exact[x]);
+                const int rt = __reduce_add_sync(0xFFFFFFFFu, ss.ret[x]);
+                unsigned long long ls = ss.len_sum[x];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xFFFFFFFFu, ls, o);
+                if (lane == 0) {
+                    wa[WA_EPISODES] += ne; wa[WA_COLLISIONS] += nc; wa[WA_SUCCESSES] += ns; wa[WA_LEN_SUM] += (long long)ls;
+                    wa[WA_RETURN] += rt; wa[WA_COLD] += ncold; wa[WA_EXACT] += nx;
+                }
+            }
             if (lane == 0) {
-                add64(s_acc, AG_ST_ENV_STEPS, (long long)n_act * K);
-                if (A.diag != nullptr) { add64(s_acc, AG_ST_COUNT + AG_DIAG_WARP_EXITS, s_exits[x >> 5]); s_exits[x >> 5] = 0; }
+                wa[WA_ENV_STEPS] += (long long)n_act * K;
+                wa[WA_EXITS] += s_exits[x >> 5]; s_exits[x >> 5] = 0;
             }
             break;
         }
@@ -568,12 +823,19 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
     prev = __shfl_sync(0xFFFFFFFFu, prev, 0);
     if (prev == LW - 1) {
         __threadfence_block();
+        // slot of s_acc -> column of s_wacc that also feeds it (-1: none)
+        const int wa_of_stat[AG_ST_COUNT] = {WA_EPISODES, WA_COLLISIONS, WA_SUCCESSES, WA_ENV_STEPS, WA_LEN_SUM, WA_RETURN, -1, -1};
+        const int wa_of_diag[AG_DIAG_COUNT] = {WA_EXACT, WA_COLD, WA_EXITS};
         if (lane < AG_ST_COUNT && A.stats != nullptr) {
-            const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(&s_acc[lane]);
+            unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(&s_acc[lane]);
+            const int col = wa_of_stat[lane];
+            if (col >= 0)
+                for (int w = 0; w < LW; ++w) v += (unsigned long long)*reinterpret_cast<volatile long long *>(&s_wacc[w][col]);
             if (v != 0) atomicAdd(&A.stats[lane], v);
         }
         if (A.diag != nullptr && lane < AG_DIAG_COUNT) {
-            const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(&s_acc[AG_ST_COUNT + lane]);
+            unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(&s_acc[AG_ST_COUNT + lane]);
+            for (int w = 0; w < LW; ++w) v += (unsigned long long)*reinterpret_cast<volatile long long *>(&s_wacc[w][wa_of_diag[lane]]);
             if (v != 0) atomicAdd(&A.diag[lane], v);
         }
         unsigned int *const sched = g_tile_sched + 2 * L.slot;
@@ -592,9 +854,9 @@ int sm_slots(const void *kernel, size_t smem) {
     return sms * occ;
 }
 
-template <bool HA, bool REC, bool M3>
+template <bool HA, bool REC, bool M3, bool CM>
 ag_status launch_t(const ag_params &P, const GridDev &G, const RolloutDev &A, const LutConst &L, size_t smem, cudaStream_t s) {
-    auto k = k_rollout_lut<HA, REC, M3>;
+    auto k = k_rollout_lut<HA, REC, M3, CM>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (ag_status)e;
     const int slots = sm_slots(reinterpret_cast<const void *>(k), smem);
@@ -618,6 +880,84 @@ bool rollout_lut_applies(const ag_params &P, const GridDev &G, const RolloutDev 
     return !legacy && G.stage && G.n_grids == 1 && G.S <= 32 && !P.choose_j_tar && (!rec || A.zfill) && budget;
 }
 
+// ---- the library-owned buffers of the configuration-space maps: a few entries per process, found by (device, grid
+// pointers, parameters); the CONTENT is validated on the device by every launch (k_cspace_build), so a grid that was
+// rewritten in place, or a new grid at a recycled address, just rebuilds the entry.
+namespace {
+struct CmapEntry {
+    int dev = -1;
+    const void *bits = nullptr, *min_x = nullptr;
+    double par[6] = {0, 0, 0, 0, 0, 0};
+    int S = 0;
+    uint32_t *buf = nullptr;
+    unsigned long long last_use = 0;
+};
+constexpr int CMAP_ENTRIES = 8;
+std::mutex g_cmap_mutex;
+CmapEntry g_cmap[CMAP_ENTRIES];
+unsigned long long g_cmap_clock = 0;
+
+// the entry's device buffer (header + map), or nullptr when the map form cannot be used for this launch
+uint32_t *cmap_buffer(const ag_params &P, const GridDev &G, cudaStream_t s) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    const double par[6] = {P.link_1, P.link_2, P.target_x, P.target_y, P.reach_eps, G.side};
+    std::lock_guard<std::mutex> lock(g_cmap_mutex);
+    CmapEntry *hit = nullptr, *lru = &g_cmap[0];
+    for (CmapEntry &e : g_cmap) {
+        if (e.buf != nullptr && e.dev == dev && e.bits == G.bits && e.min_x == G.min_x && e.S == G.S &&
+            std::memcmp(e.par, par, sizeof(par)) == 0) { hit = &e; break; }
+        if (e.last_use < lru->last_use) lru = &e;
+    }
+    if (hit == nullptr) {
+        if (capturing) return nullptr;                        // no allocation / synchronisation inside a stream capture
+        if (lru->buf != nullptr) {
+            // the buffer changes hands: launches that still read the old map (any stream of its device) must be done
+            int cur = dev;
+            if (lru->dev != cur && cudaSetDevice(lru->dev) != cudaSuccess) return nullptr;
+            cudaDeviceSynchronize();
+            if (lru->dev != cur) { cudaFree(lru->buf); lru->buf = nullptr; cudaSetDevice(cur); }
+        }
+        if (lru->buf == nullptr && cudaMalloc(&lru->buf, (size_t)(CMAP_HDR_WORDS + CMAP_WORDS) * 4) != cudaSuccess) {
+            cudaGetLastError();
+            lru->buf = nullptr; lru->dev = -1;
+            return nullptr;
+        }
+        if (cudaMemsetAsync(lru->buf, 0, CMAP_HDR_WORDS * 4, s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        lru->dev = dev; lru->bits = G.bits; lru->min_x = G.min_x; lru->S = G.S;
+        std::memcpy(lru->par, par, sizeof(par));
+        hit = lru;
+    }
+    hit->last_use = ++g_cmap_clock;
+    return hit->buf;
+}
+}  // namespace
+
+int64_t cspace_map_words(int32_t *b1, int32_t *b2) {
+    if (b1) *b1 = CB1;
+    if (b2) *b2 = CB2;
+    return CMAP_WORDS;
+}
+
+// the map alone, into a caller's buffer (ag_cspace_map): built in a scratch buffer with the header in front
+ag_status launch_cspace_map(const ag_params &P, const GridDev &G, uint32_t *map, cudaStream_t s) {
+    uint32_t *buf = nullptr;
+    cudaError_t e = cudaMallocAsync(&buf, (size_t)(CMAP_HDR_WORDS + CMAP_WORDS) * 4, s);
+    if (e != cudaSuccess) return (ag_status)e;
+    e = cudaMemsetAsync(buf, 0, CMAP_HDR_WORDS * 4, s);
+    if (e == cudaSuccess) {
+        k_cspace_build<<<CMAP_BUILD_BLOCKS, 256, 0, s>>>(P, G, buf, 0);
+        ag_note_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(map, buf + CMAP_HDR_WORDS, (size_t)CMAP_WORDS * 4, cudaMemcpyDeviceToDevice, s);
+    cudaFreeAsync(buf, s);
+    return (ag_status)e;
+}
+
 ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem_grid, cudaStream_t s) {
     LutConst L;
     L.phase_scale = 4294967296.0 / TWO_PI;
@@ -626,11 +966,28 @@ ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const Rollout
     static std::atomic<unsigned> next_slot{0};
     L.slot = next_slot.fetch_add(1, std::memory_order_relaxed) % AG_TILE_SLOTS;
     L.ss_off = (uint32_t)((smem_grid + 15) & ~(size_t)15);
-    const size_t smem = (size_t)L.ss_off + sizeof(SlowShared);
+    size_t smem = (size_t)L.ss_off + sizeof(SlowShared);
     const bool ha = A.actions != nullptr, rec = A.rec_j1 != nullptr;
     // the unrolled form tests three squares (scene_0's map); fewer are padded with far-away ones in the kernel
     const bool m3 = A.max_occupied >= 0 && A.max_occupied <= 3;
-#define AG_LUT(HA, REC) (m3 ? launch_t<HA, REC, true>(P, G, A, L, smem, s) : launch_t<HA, REC, false>(P, G, A, L, smem, s))
+    // The map form: scene-wide target only (the map holds the target box), |link| small enough for the build's margins
+    static const bool no_cmap = std::getenv("AG_ROLLOUT_NO_CMAP") != nullptr;
+    L.cmap = nullptr; L.cmap_off = 0;
+    if (!no_cmap && A.targets == nullptr) {
+        uint32_t *buf = cmap_buffer(P, G, s);
+        if (buf != nullptr) {
+            static std::atomic<unsigned> next_build{0};
+            k_cspace_build<<<CMAP_BUILD_BLOCKS, 256, 0, s>>>(P, G, buf, next_build.fetch_add(1, std::memory_order_relaxed) % CMAP_SLOTS);
+            ag_note_launch();
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return (ag_status)e;
+            L.cmap = buf + CMAP_HDR_WORDS;
+            L.cmap_off = (uint32_t)((smem + 15) & ~(size_t)15);
+            smem = (size_t)L.cmap_off + (size_t)CMAP_WORDS * 4;
+        }
+    }
+#define AG_LUT(HA, REC) (L.cmap ? launch_t<HA, REC, false, true>(P, G, A, L, smem, s) \
+                                : (m3 ? launch_t<HA, REC, true, false>(P, G, A, L, smem, s) : launch_t<HA, REC, false, false>(P, G, A, L, smem, s)))
     if (ha) return rec ? AG_LUT(true, true) : AG_LUT(true, false);
     return rec ? AG_LUT(false, true) : AG_LUT(false, false);
 #undef AG_LUT

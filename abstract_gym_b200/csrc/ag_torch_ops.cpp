@@ -53,7 +53,7 @@ ag_params unpack_params(const Tensor &p) {
     return q;
 }
 
-ag_grid make_grid(const Tensor &bits, const OptTensor &bits_t, const Tensor &min_x, const Tensor &min_y, double side,
+ag_grid make_grid(const Tensor &bits, const OptTensor &bits_t, const OptTensor &hier, const Tensor &min_x, const Tensor &min_y, double side,
                   double env_size, int64_t S, int64_t n_grids, int64_t max_occupied, int64_t envs_per_grid, c10::Device dev) {
     need(bits, at::kInt, "grid_bits", dev);
     need(min_x, at::kDouble, "min_x", dev);
@@ -62,6 +62,9 @@ ag_grid make_grid(const Tensor &bits, const OptTensor &bits_t, const Tensor &min
     ag_grid g;
     g.bits = reinterpret_cast<const uint32_t *>(bits.data_ptr());
     g.bits_t = opt_ptr<const uint32_t>(bits_t, at::kInt, "grid_bits_t", dev);
+    g.hier = opt_ptr<const void>(hier, at::kByte, "grid_hier", dev);
+    TORCH_CHECK(g.hier == nullptr || hier->numel() == n_grids * ag_grid_hier_bytes((int32_t)S),
+                "grid_hier must hold n_grids * ag_grid_hier_bytes(S) bytes (ag_grid_pack_hier)");
     g.min_x = min_x.data_ptr<double>(); g.min_y = min_y.data_ptr<double>();
     g.side = side; g.env_size = env_size;
     g.S = (int32_t)S; g.words_per_row = ag_grid_words_per_row((int32_t)S);
@@ -75,7 +78,7 @@ ag_grid make_grid(const Tensor &bits, const OptTensor &bits_t, const Tensor &min
 void *stream_of(c10::Device dev) { return c10::cuda::getCurrentCUDAStream(dev.index()).stream(); }
 
 // Scene.collision_check (scenario/scene_0.py:60-76) -> ag_collision_check
-void collision_check(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const Tensor &min_x, const Tensor &min_y,
+void collision_check(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const OptTensor &hier, const Tensor &min_x, const Tensor &min_y,
                      double side, double env_size, int64_t S, int64_t n_grids, int64_t max_occupied, int64_t envs_per_grid,
                      const Tensor &j1, const Tensor &j2, Tensor hit, OptTensor first_hit, int64_t env_id0, int64_t engine) {
     const c10::Device dev = j1.device();
@@ -83,14 +86,14 @@ void collision_check(const Tensor &params, const Tensor &bits, const OptTensor &
     need(j1, at::kDouble, "j1", dev); need(j2, at::kDouble, "j2", dev); need(hit, at::kByte, "hit", dev);
     TORCH_CHECK(j2.numel() == j1.numel() && hit.numel() == j1.numel(), "j1, j2, hit must have one element per env");
     const ag_params p = unpack_params(params);
-    const ag_grid g = make_grid(bits, bits_t, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
+    const ag_grid g = make_grid(bits, bits_t, hier, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
     check_status(ag_collision_check(&p, &g, j1.data_ptr<double>(), j2.data_ptr<double>(), hit.data_ptr<uint8_t>(),
                                     opt_ptr<int32_t>(first_hit, at::kInt, "first_hit", dev), j1.numel(), env_id0,
                                     (int32_t)engine, stream_of(dev)), "ag_collision_check");
 }
 
 // Scene.step (scenario/scene_0.py:88-103) -> ag_step
-void step(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const Tensor &min_x, const Tensor &min_y, double side,
+void step(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const OptTensor &hier, const Tensor &min_x, const Tensor &min_y, double side,
           double env_size, int64_t S, int64_t n_grids, int64_t max_occupied, int64_t envs_per_grid, Tensor j1, Tensor j2,
           const Tensor &actions, Tensor reward, Tensor flags, OptTensor ee, OptTensor dist, OptTensor first_hit, OptTensor stats,
           const OptTensor &targets, int64_t env_id0, int64_t engine) {
@@ -103,7 +106,7 @@ void step(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, con
                 (actions.scalar_type() == at::kFloat || actions.scalar_type() == at::kDouble),
                 "actions must be a contiguous CUDA [N,2] float32 or float64 tensor");
     const ag_params p = unpack_params(params);
-    const ag_grid g = make_grid(bits, bits_t, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
+    const ag_grid g = make_grid(bits, bits_t, hier, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
     check_status(ag_step(&p, &g, j1.data_ptr<double>(), j2.data_ptr<double>(), actions.data_ptr(),
                          actions.scalar_type() == at::kFloat ? 1 : 0, reward.data_ptr<float>(), flags.data_ptr<uint8_t>(),
                          opt_ptr<double>(ee, at::kDouble, "ee", dev), opt_ptr<double>(dist, at::kDouble, "dist", dev),
@@ -113,7 +116,7 @@ void step(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, con
 }
 
 // Scene.reset / random_valid_pose (scenario/scene_0.py:105-113,174-181) -> ag_reset
-void reset(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const Tensor &min_x, const Tensor &min_y, double side,
+void reset(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const OptTensor &hier, const Tensor &min_x, const Tensor &min_y, double side,
            double env_size, int64_t S, int64_t n_grids, int64_t max_occupied, int64_t envs_per_grid, Tensor j1, Tensor j2,
            Tensor reward, Tensor flags, Tensor reset_ctr, const OptTensor &mask, const OptTensor &reset_u, OptTensor stats,
            int64_t seed, bool clear_flags, int64_t env_id0, int64_t engine) {
@@ -128,7 +131,7 @@ void reset(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, co
         R = (int32_t)reset_u->size(1);
     }
     const ag_params p = unpack_params(params);
-    const ag_grid g = make_grid(bits, bits_t, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
+    const ag_grid g = make_grid(bits, bits_t, hier, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
     check_status(ag_reset(&p, &g, j1.data_ptr<double>(), j2.data_ptr<double>(), reward.data_ptr<float>(), flags.data_ptr<uint8_t>(),
                           reinterpret_cast<uint32_t *>(reset_ctr.data_ptr()), opt_ptr<const uint8_t>(mask, at::kByte, "mask", dev),
                           opt_ptr<const double>(reset_u, at::kDouble, "reset_u", dev), R, (uint64_t)seed, clear_flags ? 1 : 0,
@@ -137,7 +140,7 @@ void reset(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, co
 }
 
 // the loop body of experiment/experiment_0.py:20-34 fused over K steps -> ag_rollout
-void rollout(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const Tensor &min_x, const Tensor &min_y, double side,
+void rollout(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const OptTensor &hier, const Tensor &min_x, const Tensor &min_y, double side,
              double env_size, int64_t S, int64_t n_grids, int64_t max_occupied, int64_t envs_per_grid, Tensor j1, Tensor j2,
              Tensor reward, Tensor flags, Tensor step_ctr, Tensor reset_ctr, Tensor ep_len, const OptTensor &actions,
              const OptTensor &reset_u, const OptTensor &targets, OptTensor rec_j1, OptTensor rec_j2, OptTensor rec_reward,
@@ -175,12 +178,12 @@ void rollout(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, 
     a.event_count = opt_ptr<int64_t>(event_count, at::kLong, "event_count", dev);
     if (a.events) a.event_capacity = events->numel() / 3;
     const ag_params p = unpack_params(params);
-    const ag_grid g = make_grid(bits, bits_t, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
+    const ag_grid g = make_grid(bits, bits_t, hier, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
     check_status(ag_rollout(&p, &g, &a, stream_of(dev)), "ag_rollout");
 }
 
 // fused gym-style step (scenario/vector_env.py): Scene.step + same-step auto-reset + observations -> ag_step_obs
-void step_obs(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const Tensor &min_x, const Tensor &min_y, double side,
+void step_obs(const Tensor &params, const Tensor &bits, const OptTensor &bits_t, const OptTensor &hier, const Tensor &min_x, const Tensor &min_y, double side,
               double env_size, int64_t S, int64_t n_grids, int64_t max_occupied, int64_t envs_per_grid, Tensor j1, Tensor j2,
               const Tensor &actions, Tensor reward, Tensor flags, Tensor reset_ctr, Tensor ep_len, const OptTensor &targets, Tensor obs,
               Tensor reward_out, Tensor terminated, Tensor collision, OptTensor final_obs, OptTensor crop, Tensor stats, int64_t seed,
@@ -203,7 +206,7 @@ void step_obs(const Tensor &params, const Tensor &bits, const OptTensor &bits_t,
         crop_size = (int32_t)crop->size(1);
     }
     const ag_params p = unpack_params(params);
-    const ag_grid g = make_grid(bits, bits_t, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
+    const ag_grid g = make_grid(bits, bits_t, hier, min_x, min_y, side, env_size, S, n_grids, max_occupied, envs_per_grid, dev);
     check_status(ag_step_obs(&p, &g, j1.data_ptr<double>(), j2.data_ptr<double>(), actions.data_ptr(),
                              actions.scalar_type() == at::kFloat ? 1 : 0, reward.data_ptr<float>(), flags.data_ptr<uint8_t>(),
                              reinterpret_cast<uint32_t *>(reset_ctr.data_ptr()), reinterpret_cast<uint32_t *>(ep_len.data_ptr()),
@@ -215,7 +218,7 @@ void step_obs(const Tensor &params, const Tensor &bits, const OptTensor &bits_t,
                  "ag_step_obs");
 }
 
-#define AG_GRID_SCHEMA "Tensor params, Tensor grid_bits, Tensor? grid_bits_t, Tensor min_x, Tensor min_y, float side, float env_size, " \
+#define AG_GRID_SCHEMA "Tensor params, Tensor grid_bits, Tensor? grid_bits_t, Tensor? grid_hier, Tensor min_x, Tensor min_y, float side, float env_size, " \
                        "int S, int n_grids, int max_occupied, int envs_per_grid, "
 
 }  // namespace

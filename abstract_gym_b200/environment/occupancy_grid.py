@@ -8,6 +8,8 @@ row 0 is the TOP row; the grid is not centred.
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 
@@ -21,13 +23,26 @@ def _wants_transposed(S, stride_words):
     fit the kernels' shared-memory staging window (32 KB; e.g. the 256x256 per-batch maps: 2 x 8 KB); for a grid
     that stays in global memory (1024x1024: 2 x 128 KB) the second array only thrashes L1 (measured: 261 -> 292 ms)."""
     spad = (S + 1) & ~1
-    return S > 32 and 16 + 2 * stride_words * 4 + spad * 16 <= 32768
+    form = os.environ.get("AG_GRID_FORM", "")
+    if form:
+        return form == "transposed"
+    return 32 < S < 64 and 16 + 2 * stride_words * 4 + spad * 16 <= 32768
+
+
+def _wants_hier(S):
+    """The two-level form (8x8 tiles + summary bitmap, ag_grid.hier) for every map beyond the obstacle-list class:
+    the FAST engine then walks S/8 summary lines per link instead of S (measured on configs 4 / 5: DESIGN.md)."""
+    form = os.environ.get("AG_GRID_FORM", "")
+    if form:
+        return form == "hier"
+    return S >= 64
 
 
 class DeviceGrid:
     """What the kernels read: bits[n_grids][stride_words] uint32, min_x[S], min_y[S] float64."""
 
-    def __init__(self, bits, S, environment_size, n_grids=1, envs_per_grid=1 << 62, max_occupied=None, bits_t=None):
+    def __init__(self, bits, S, environment_size, n_grids=1, envs_per_grid=1 << 62, max_occupied=None, bits_t=None,
+                 hier=None):
         lib = _lib.load()
         self.device = bits.device
         self.S = int(S)
@@ -40,6 +55,12 @@ class DeviceGrid:
         self.bits = bits
         self.bits_t = bits_t          # transposed copy (column-major lines) for the minor-axis traversal, or None
         self.max_occupied = -1 if max_occupied is None else int(max_occupied)
+        self.hier = hier              # two-level form (tiles + summary bitmap), uint8 [n_grids * hier_bytes], or None
+        if hier is None and _wants_hier(self.S):
+            hb = int(lib.ag_grid_hier_bytes(self.S))
+            self.hier = torch.empty(self.n_grids * hb, dtype=torch.uint8, device=self.device)
+            _lib.check(lib.ag_grid_pack_hier(ptr(self.bits), self.S, self.n_grids, self.stride_words, ptr(self.hier),
+                                             stream_ptr(self.device)), "ag_grid_pack_hier")
         spad = (self.S + 1) & ~1
         mx = np.zeros(spad, dtype=np.float64)
         my = np.zeros(spad, dtype=np.float64)
@@ -60,6 +81,7 @@ class DeviceGrid:
         g.grid_stride_words = self.stride_words
         g.envs_per_grid = self.envs_per_grid if envs_per_grid is None else int(envs_per_grid)
         g.bits_t = None if self.bits_t is None else self.bits_t.data_ptr()
+        g.hier = None if self.hier is None else self.hier.data_ptr()
         return g
 
     @classmethod

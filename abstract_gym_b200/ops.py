@@ -9,7 +9,7 @@ network.
 
 Every op starts with the same eleven scene / grid arguments:
     params        float64[13] CPU tensor  = pack_params(scene.params())      (ag_params)
-    grid_bits     int32 [n_grids * stride] CUDA, grid_bits_t (optional transposed planes), min_x, min_y float64 [>= S]
+    grid_bits     int32 [n_grids * stride] CUDA, grid_bits_t (optional transposed planes), grid_hier (optional two-level form, uint8), min_x, min_y float64 [>= S]
     side, env_size, S, n_grids, max_occupied, envs_per_grid                   = grid_args(device_grid)
 The object API (`BatchedScene`, `VectorEnv`) is the convenient front end; these ops are the functional one.
 """
@@ -45,8 +45,8 @@ def pack_params(p: _lib.Params) -> torch.Tensor:
 
 
 def grid_args(dg):
-    """dg: abstract_gym_b200.DeviceGrid -> the ten grid arguments every op takes after `params`"""
-    return (dg.bits, dg.bits_t, dg.min_x, dg.min_y, float(dg.side), float(dg.environment_size), int(dg.S), int(dg.n_grids),
+    """dg: abstract_gym_b200.DeviceGrid -> the eleven grid arguments every op takes after `params`"""
+    return (dg.bits, dg.bits_t, dg.hier, dg.min_x, dg.min_y, float(dg.side), float(dg.environment_size), int(dg.S), int(dg.n_grids),
             int(dg.max_occupied), int(dg.envs_per_grid))
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define AG_ABI_VERSION 4
+#define AG_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define AG_API __attribute__((visibility("default")))
@@ -83,6 +83,13 @@ typedef struct ag_grid {
                                       * bits_t[g*grid_stride_words + c*words_per_row + r/32] is cell (row r, col c), i.e.
                                       * ag_grid_pack of the transposed matrices; NULL = none.  With it the FAST engine walks
                                       * a link along its minor axis (columns for shallow links) instead of always by rows. */
+    const void *hier;                /* optional two-level form of the same bits, ag_grid_hier_bytes(S) bytes per grid, written
+                                      * by ag_grid_pack_hier (NULL = none).  With T = ceil(S/8): first T*T uint64 "tiles" (padded
+                                      * to an even count), tile (R, C) holding the 8x8 block of cells with bit (r%8)*8 + c%8 for
+                                      * cell (8R + r%8, 8C + c%8); then a T x T summary bitmap, ceil(T/32) words per row (padded
+                                      * to a multiple of 4 words), bit C%32 of word R*ceil(T/32) + C/32 set iff tile (R, C) has
+                                      * an occupied cell.  With it the FAST engine walks a link over the summary (8x fewer lines)
+                                      * and looks at the cells of occupied tiles only. */
 } ag_grid;
 
 /* Collision engine selection. All three return identical flags (tests/test_gpu_parity.py):
@@ -123,6 +130,7 @@ AG_API const char *ag_status_string(ag_status s);
 AG_API void ag_default_params(ag_params *p);
 AG_API int32_t ag_grid_words_per_row(int32_t S);
 AG_API int64_t ag_grid_stride_words(int32_t S);
+AG_API int64_t ag_grid_hier_bytes(int32_t S);    /* size of ag_grid.hier per grid (a multiple of 16) */
 
 /* OccupancyGrid.__init__/load_from_matrix -> packed bits (occupancy_grid.py:25-50,73-93).
  * occ: rows x cols uint8 host matrix (non-zero = occupied); bits_out: ag_grid_stride_words(S) words. */
@@ -135,6 +143,10 @@ AG_API ag_status ag_grid_tables_host(int32_t S, double env_size, double *min_x, 
 /* K5: pack n_grids S x S uint8 occupancy matrices (device) into bits (device). */
 AG_API ag_status ag_grid_pack(const uint8_t *occ, int32_t S, int32_t n_grids, uint32_t *bits,
                        int64_t grid_stride_words, void *stream);
+/* the two-level form (ag_grid.hier) of n_grids packed grids: bits (device) -> hier (device, 16-byte aligned,
+ * n_grids * ag_grid_hier_bytes(S) bytes) */
+AG_API ag_status ag_grid_pack_hier(const uint32_t *bits, int32_t S, int32_t n_grids, int64_t grid_stride_words, void *hier,
+                            void *stream);
 
 /* utils/geometry.py:14-32 Line.compute_line_function() and utils/collision_checker.py:12-46
  * CollisionChecker(line, square).compute_corner_line_value()/.collision_check() over arrays.
@@ -243,6 +255,17 @@ typedef struct ag_rollout_args {
 } ag_rollout_args;
 
 AG_API ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream);
+
+/* The configuration-space map ag_rollout consults for scene_0-class grids (one staged grid of at most 8 occupied
+ * cells, S <= 32, FAST engine, scene-wide cartesian target): one bit per bin of (joint_1, joint_2) mod 2 pi,
+ * 2^*b1 x 2^*b2 bins; bit (i1 << *b2 | i2) is bit (i & 31) of word i >> 5.  CLEAR means: for every pose of the bin,
+ * Scene.collision_check() is False and check_target_reached() is False (scenario/scene_0.py:60-76,129-130), so a step
+ * that lands there is uneventful; SET means "evaluate".  ag_rollout builds and caches the map itself (validated against
+ * the current grid and parameters at every launch); this entry point builds it into a caller's device buffer of
+ * ag_cspace_map_words() uint32 words -- it exists for inspection and for tests/test_gpu_parity.py, which checks the
+ * CLEAR guarantee against the BRUTE engine. */
+AG_API int64_t ag_cspace_map_words(int32_t *b1, int32_t *b2);
+AG_API ag_status ag_cspace_map(const ag_params *p, const ag_grid *g, uint32_t *map, void *stream);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 AG_API int64_t ag_launch_count(void);

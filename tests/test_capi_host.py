@@ -29,7 +29,7 @@ def test_header_symbols_exported(lib):
 def test_struct_layouts_match_header():
     from abstract_gym_b200 import _lib
     assert C.sizeof(_lib.Params) == 11 * 8 + 2 * 4
-    assert C.sizeof(_lib.Grid) == 3 * 8 + 2 * 8 + 4 * 4 + 2 * 8 + 8
+    assert C.sizeof(_lib.Grid) == 3 * 8 + 2 * 8 + 4 * 4 + 2 * 8 + 8 + 8
     assert C.sizeof(_lib.RolloutArgs) == 8 + 8 + 4 + 4 + 8 + 8 + 8 + 4 + 4 + 14 * 8 + 8 + 8 + 8 + 4 + 4
 
 

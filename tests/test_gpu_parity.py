@@ -579,7 +579,7 @@ def test_tangency_band_all_engines_and_oracle(ag, torch_, oracle):
 @pytest.mark.gpu
 def test_torch_custom_ops_equal_object_api(ag, torch_):
     """torch.ops.abstract_gym_b200.* -- the COMPILED op library (csrc/ag_torch_ops.cpp over the same C symbols) ==
-    BatchedScene, on scene_0's map and on per-batch 256x256 maps with transposed planes, scripted reset candidates,
+    BatchedScene, on scene_0's map and on per-batch 256x256 maps in the two-level form, scripted reset candidates,
     per-env targets, a statistics-only rollout and the filter diagnostics; CPU tensors are refused."""
     import time
     from abstract_gym_b200 import ops, build
@@ -599,7 +599,7 @@ def test_torch_custom_ops_equal_object_api(ag, torch_):
         rec = ref.rollout(K, actions=acts, reset_u=ru, targets=tg)
         sc = make_scene(ag, torch_, g, j1, j2, seed=3)         # only used as a bag of correctly typed state tensors
         dg = sc.grid
-        assert (dg.bits_t is not None) == (kind == "c5")
+        assert (dg.hier is not None) == (kind == "c5")
         P, GA = ops.pack_params(sc.params()), ops.grid_args(dg)
         out = sc.alloc_records(K)
         hit = torch_.empty(n, dtype=torch_.uint8, device="cuda")
@@ -1252,3 +1252,80 @@ def test_debug_bounds_build(ag, torch_):
     r = subprocess.run([sys.executable, "-c", code, "trap"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True, timeout=300)
     assert r.returncode == 3 and "AG_DEBUG_BOUNDS" in r.stdout and "trapped" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["scene0", "scene0_long_links", "random_small"])
+def test_cspace_map_clear_bins_are_uneventful(ag, torch_, case):
+    """the configuration-space map of the headline rollout kernel (include/abstract_gym_b200.h ag_cspace_map): a CLEAR
+    bit promises collision_check() == False and check_target_reached() == False for every pose of the bin.  Checked
+    against the BRUTE engine (the reference's loop over all obstacles, float64) on 4M poses per case: uniform ones,
+    poses around scene_0's tangent configurations (link 1 along an axis) and poses on bin edges."""
+    import ctypes as C
+    import math
+    from abstract_gym_b200 import _lib
+    from abstract_gym_b200._device import ptr, stream_ptr
+    torch = torch_
+    lib = _lib.load()
+    b1, b2 = C.c_int32(), C.c_int32()
+    words = lib.ag_cspace_map_words(C.byref(b1), C.byref(b2))
+    b1, b2 = b1.value, b2.value
+    assert words * 32 == 1 << (b1 + b2)
+    rng = np.random.default_rng(21)
+    link = (0.4, 0.3)
+    if case == "scene0":
+        grid, target = ag.OccupancyGrid(size=9, random_obstacle=False), None
+    elif case == "scene0_long_links":
+        grid, target, link = ag.OccupancyGrid(size=9, random_obstacle=False), (0.35, 0.55), (0.45, 0.4)
+    else:
+        occ = np.zeros((17, 17), np.uint8)
+        occ[rng.integers(0, 17, 7), rng.integers(0, 17, 7)] = 1
+        occ[8, 8] = occ[9, 8] = 0
+        grid, target = ag.OccupancyGrid(size=17, random_obstacle=False), (-0.31, 0.22)
+        grid.load_from_matrix(occ)
+    n = 1 << 22
+    q1, q2 = rng.uniform(-20.0, 20.0, n), rng.uniform(-20.0, 20.0, n)
+    k = n // 4                                                    # tangent poses of link 1: k*pi/2 +- 10^-9 .. 10^-1
+    q1[:k] = rng.integers(-8, 8, k) * (math.pi / 2) + rng.choice([-1.0, 1.0], k) * 10.0 ** rng.uniform(-9, -1, k)
+    e = n // 8                                                    # poses on bin edges (both joints), +- a few phase units
+    q1[k:k + e] = rng.integers(0, 1 << b1, e) * (2 * math.pi / (1 << b1)) + rng.uniform(-3e-9, 3e-9, e)
+    q2[k:k + e] = rng.integers(0, 1 << b2, e) * (2 * math.pi / (1 << b2)) + rng.uniform(-3e-9, 3e-9, e)
+    robot = ag.BatchedTwoJointRobot(torch.as_tensor(q1, device="cuda"), torch.as_tensor(q2, device="cuda"), link_1=link[0], link_2=link[1])
+    kw = {} if target is None else dict(target_c=ag.Point(*target))
+    sc = ag.BatchedScene(robot, grid, engine="brute", **kw)
+    m = torch.zeros(words, dtype=torch.int32, device="cuda")
+    _lib.check(lib.ag_cspace_map(sc.params(), sc.grid.c_struct(), ptr(m), stream_ptr(sc.device)), "ag_cspace_map")
+    eventful = (sc.collision_check() | sc.check_target_reached()).cpu().numpy()
+    mw = m.cpu().numpy().view(np.uint32)
+    # the kernel's phase: low 32 bits of round(q * 2^32 / 2pi); numpy's product rounds twice (fma does not), which moves
+    # a pose by at most one phase unit (1.5e-9 rad) -- far inside the map's 2e-6 m margin
+    scale = 4294967296.0 / (2 * math.pi)
+    x1 = np.rint(q1 * scale).astype(np.int64) & 0xFFFFFFFF
+    x2 = np.rint(q2 * scale).astype(np.int64) & 0xFFFFFFFF
+    bit = ((x1 >> (32 - b1)) << b2) | (x2 >> (32 - b2))
+    is_set = ((mw[bit >> 5] >> (bit & 31).astype(np.uint32)) & 1).astype(bool)
+    bad = eventful & ~is_set
+    assert not bad.any(), "%d eventful poses in CLEAR bins, e.g. q = (%r, %r)" % (bad.sum(), q1[bad][0], q2[bad][0])
+    uni = slice(k + e, n)
+    frac = (is_set[uni] & ~eventful[uni]).sum() / max((~eventful[uni]).sum(), 1)
+    print("cspace map %s: %d x %d bins, %.2f %% of them set; %.3f %% of the uneventful uniform poses sit in SET bins"
+          % (case, 1 << b1, 1 << b2, 100 * is_set[uni].mean(), 100 * frac))
+    assert frac < 0.03
+    assert eventful.sum() > 1000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["rows", "transposed", "hier"])
+def test_grid_forms_rollout_vs_oracle(ag, torch_, oracle, form, monkeypatch):
+    """the three traversal forms of the FAST engine for maps beyond the obstacle-list class -- row-major bits, rows +
+    transposed copy (minor-axis walk), two-level tiles + summary bitmap (ag_grid.hier) -- each against the oracle:
+    sizes that are and are not multiples of 8 / 32, one global map and staged per-batch maps, dense and sparse."""
+    monkeypatch.setenv("AG_GRID_FORM", form)
+    rng = np.random.default_rng(77)
+    for S, p, n_maps, n, K in ((64, 0.02, 1, 2048, 10), (100, 0.01, 4, 2048, 10), (257, 0.004, 2, 1024, 8), (520, 0.002, 1, 1024, 6)):
+        occs = [random_grid(rng, S, p) for _ in range(n_maps)]
+        stats = _rollout_case(ag, torch_, oracle, occs, n, K, "fast", scripted=True, envs_per_grid=n // n_maps)
+        assert stats[0] > 0
+        g = ag.BatchedOccupancyGrid(torch_.as_tensor(np.stack(occs), device="cuda"), n // n_maps)
+        dg = g.device_grid("cuda") if hasattr(g, "device_grid") else g._grid
+        assert (dg.hier is not None) == (form == "hier") and (dg.bits_t is not None) == (form == "transposed")
