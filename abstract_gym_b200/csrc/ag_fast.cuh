@@ -394,42 +394,24 @@ __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, co
 // whose set bits go to the narrow phase (narrow_f32's first test discards the cells the line misses in ~15
 // instructions).  Tile coordinates: fine column c = round(u) with u = x*inv_side + xoff covers u in [c-1/2, c+1/2), so
 // tile column C = c >> 3 covers (u + 1/2)/8 - 1/2 in [C-1/2, C+1/2); rows alike.
-__device__ __forceinline__ bool scan_tiles(const GridDev &G, const GridView &V, uint32_t word, int w, int line, LinkScan &K) {
-    while (word) {
-        const int tc = (w << 5) + __ffs(word) - 1;
-        word &= word - 1;
-        AG_CHECK_INDEX(line * G.T + tc, G.T * G.T);
-        unsigned long long tile = V.tiles[line * G.T + tc];
-        while (tile) {
-            const int b = __ffsll((long long)tile) - 1;
-            tile &= tile - 1;
-            if (!K.have_link) { K.L = make_link_f(K.p0x, K.p0y, K.p1x, K.p1y, K.side); K.have_link = true; }
-            const int r = (line << 3) + (b >> 3), c = (tc << 3) + (b & 7);
-            AG_CHECK_INDEX(r, G.S); AG_CHECK_INDEX(c, G.S);
-            const float mnx = (float)V.min_x[c], mny = (float)V.min_y[r];
-            const int v = narrow_f32(K.L, mnx, mny, mnx + K.side, mny + K.side);
-            if (v == 1) return true;
-            K.result |= v;          // 0 or 2
-        }
-    }
-    return false;
-}
+//
+// Two phases per pose, because the lanes of a warp meet their occupied tiles on different lines: with the narrow phase
+// nested in the line loop every line trip ran ~80 instructions for the few lanes that had a tile there while the others
+// waited (profiles/r2 "h_c4": 2.8 threads per instruction in that part, 5.1 overall).  Phase A walks the summary lines
+// of BOTH links and only pushes the occupied tiles (tile index | link << 15) onto a per-lane queue in shared memory;
+// phase B drains the queue, so all lanes run the narrow phase together.
+// A cell the float32 narrow phase cannot settle is settled on the spot by the reference predicate in float64
+// (segment_square_exact on the float64 arm, get_arm()) -- before, one undecided cell sent the lane through the whole
+// float64 traversal of the bit grid (~4000 instructions on a 1024 x 1024 map, 17 % of all instructions of config 4).
+// Nearly axis-aligned links still return 2 (the caller's float64 path knows how the reference treats them).
+constexpr int AG_TILEQ = 24;
+constexpr int AG_TILEQ_COLS = 256;      // threads per block of every kernel that reaches the traversal (AG_BLOCK)
+constexpr int AG_HIER_MAX_T = 128;      // a queue entry is (tile row << 7 | tile column) | link << 15: S <= 1024
 
-__device__ __forceinline__ bool scan_tile_line(const GridDev &G, const GridView &V, const uint32_t *__restrict__ linep, int line,
-                                               int p_lo, int p_hi, LinkScan &K) {
-    const int w0 = p_lo >> 5, w1 = p_hi >> 5;
-    const uint32_t mlo = 0xFFFFFFFFu << (p_lo & 31), mhi = 0xFFFFFFFFu >> (31 - (p_hi & 31));
-    for (int w = w0; w <= w1; ++w) {
-        uint32_t word = linep[w];
-        if (w == w0) word &= mlo;
-        if (w == w1) word &= mhi;
-        if (word != 0 && scan_tiles(G, V, word, w, line, K)) return true;
-    }
-    return false;
-}
-
-__device__ __forceinline__ int link_fast_hier(const GridDev &G, const GridView &V, const FastConst &C, float p0x, float p0y,
-                                              float p1x, float p1y) {
+// phase A for one link: push(tile row << 7 | tile column) for every occupied tile within the link's margin
+template <typename Push>
+__device__ __forceinline__ void link_tiles(const GridDev &G, const GridView &V, const FastConst &C, float p0x, float p0y, float p1x,
+                                           float p1y, Push push) {
     // margin in tiles: the fine walk's margin (cells) / 8, plus slack for the float32 tile coordinates
     const float mcell = (fmaxf(2.0e-6f * C.inv_side, 1.0e-3f) + 0.001f) * 0.125f + 0.001f;
     const int T1 = G.T - 1;
@@ -438,38 +420,96 @@ __device__ __forceinline__ int link_fast_hier(const GridDev &G, const GridView &
     const float xoff = hi8 - 0.5f, roff = hi8 + (0.125f - 0.5f);          // ((xoff_fine + 1/2)/8 - 1/2), ((roff_fine + 1/2)/8 - 1/2)
     const float pa = fmaf(p0x, inv8, xoff), pb = fmaf(p1x, inv8, xoff);    // tile columns of the end points
     const float la = fmaf(-p0y, inv8, roff), lb = fmaf(-p1y, inv8, roff);  // tile rows of the end points
-    LinkScan K;
-    K.p0x = p0x; K.p0y = p0y; K.p1x = p1x; K.p1y = p1y; K.side = C.side; K.have_link = false; K.result = 0; K.swapped = false;
     int l_lo = round_magic(fminf(la, lb) - mcell), l_hi = round_magic(fmaxf(la, lb) + mcell);
-    if (l_lo > T1 || l_hi < 0) return 0;
+    if (l_lo > T1 || l_hi < 0) return;
     l_lo = max(l_lo, 0); l_hi = min(l_hi, T1);
     const float pseg_lo = fminf(pa, pb), pseg_hi = fmaxf(pa, pb);
     const uint32_t *linep = V.coarse + l_lo * G.cwpr;
     const float dl = lb - la, dp = pb - pa;
     const bool tracked = (l_hi - l_lo >= 2) && (fabsf(dl) * 64.0f >= fabsf(dp));
-    if (!tracked) {
-        const int p_lo = max(round_magic(pseg_lo - mcell), 0), p_hi = min(round_magic(pseg_hi + mcell), T1);
-        if (p_lo > p_hi) return 0;
-        for (int l = l_lo; l <= l_hi; ++l, linep += G.cwpr)
-            if (scan_tile_line(G, V, linep, l, p_lo, p_hi, K)) return 1;
-        return K.result;
-    }
-    // the position interval of tile row l follows the link: [p(l - 1/2), p(l + 1/2)] widened as in link_fast
-    const float s = dp * __frcp_rn(dl);
+    // the position interval of tile row l follows the link: [p(l - 1/2), p(l + 1/2)] widened as in link_fast;
+    // untracked (few lines, or a very shallow link): every line gets the link's whole position range
+    const float s = tracked ? dp * __frcp_rn(dl) : 0.0f;
     const float mm = mcell + 5.0e-5f * inv8 + fabsf(s) * mcell;
     const float clamp_lo = pseg_lo - mm, clamp_hi = pseg_hi + mm;
     const float pstart = fmaf(((float)l_lo - 0.5f) - la, s, pa);
     float pprev = pstart, k = 1.0f;
     for (int l = l_lo; l <= l_hi; ++l, linep += G.cwpr, k += 1.0f) {
-        const float pcur = fmaf(k, s, pstart);
-        const float lo = fmaxf(fminf(pprev, pcur) - mm, clamp_lo), hi = fminf(fmaxf(pprev, pcur) + mm, clamp_hi);
-        pprev = pcur;
+        float lo = clamp_lo, hi = clamp_hi;
+        if (tracked) {
+            const float pcur = fmaf(k, s, pstart);
+            lo = fmaxf(fminf(pprev, pcur) - mm, clamp_lo); hi = fminf(fmaxf(pprev, pcur) + mm, clamp_hi);
+            pprev = pcur;
+        }
         const int p_lo = max(round_magic(lo), 0), p_hi = min(round_magic(hi), T1);
         if (p_lo > p_hi) continue;
         AG_CHECK_INDEX(l, G.T); AG_CHECK_INDEX(p_lo, G.T); AG_CHECK_INDEX(p_hi, G.T);
-        if (scan_tile_line(G, V, linep, l, p_lo, p_hi, K)) return 1;
+        const int w0 = p_lo >> 5, w1 = p_hi >> 5;
+        const uint32_t mlo = 0xFFFFFFFFu << (p_lo & 31), mhi = 0xFFFFFFFFu >> (31 - (p_hi & 31));
+        for (int w = w0; w <= w1; ++w) {
+            uint32_t word = linep[w];
+            if (w == w0) word &= mlo;
+            if (w == w1) word &= mhi;
+            while (word) {
+                const int tc = (w << 5) + __ffs(word) - 1;
+                word &= word - 1;
+                push((l << 7) | tc);
+            }
+        }
     }
-    return K.result;
+}
+
+// both links of one pose: 0 / 1 certain, 2 undecided.  get_arm(): the pose's float64 arm (reference arithmetic), evaluated
+// only when a cell needs the float64 predicate; eps: CollisionChecker's section epsilon.
+template <typename GetArm>
+__device__ __forceinline__ int arm_fast_hier(const GridDev &G, const GridView &V, const FastConst &C, const ArmF &a, GetArm get_arm,
+                                             double eps) {
+    __shared__ unsigned short s_tileq[AG_TILEQ][AG_TILEQ_COLS];
+    AG_CHECK_INDEX(G.T, AG_HIER_MAX_T + 1);
+    AG_CHECK_INDEX(threadIdx.x, AG_TILEQ_COLS);
+    const int tx = threadIdx.x;
+    int cnt = 0, result = 0;
+    bool hit = false;
+    // phase B: drain this lane's queue
+    auto drain = [&]() {
+        for (int i = 0; i < cnt && !hit; ++i) {
+            const unsigned e = s_tileq[i][tx];
+            const bool second = (e >> 15) != 0;
+            const int tr = (int)((e >> 7) & 0x7Fu), tc = (int)(e & 0x7Fu);
+            AG_CHECK_INDEX(tr, G.T); AG_CHECK_INDEX(tc, G.T);
+            unsigned long long tile = V.tiles[tr * G.T + tc];
+            const LinkF L = make_link_f(second ? a.ex : 0.0f, second ? a.ey : 0.0f, second ? a.gx : a.ex, second ? a.gy : a.ey, C.side);
+            while (tile) {
+                const int b = __ffsll((long long)tile) - 1;
+                tile &= tile - 1;
+                const int r = (tr << 3) + (b >> 3), c = (tc << 3) + (b & 7);
+                AG_CHECK_INDEX(r, G.S); AG_CHECK_INDEX(c, G.S);
+                const double mnxd = V.min_x[c], mnyd = V.min_y[r];
+                const float mnx = (float)mnxd, mny = (float)mnyd;
+                int v = narrow_f32(L, mnx, mny, mnx + C.side, mny + C.side);
+                if (v == 2 && !L.degenerate) {                              // settle this cell with the reference predicate
+                    const Arm A = get_arm();
+                    const LineD Ld = second ? make_line(A.ex, A.ey, A.gx, A.gy) : make_line(0.0, 0.0, A.ex, A.ey);
+                    int axis = 0;
+                    v = segment_square_exact(Ld, mnxd, mnyd, __dadd_rn(mnxd, G.side), __dadd_rn(mnyd, G.side), eps, axis) ? 1 : 0;
+                }
+                if (v == 1) { hit = true; break; }
+                result |= v;
+            }
+        }
+        cnt = 0;
+    };
+    auto push_link = [&](unsigned link_bit) {
+        return [&, link_bit](int rc) {
+            if (cnt == AG_TILEQ) drain();                                   // rare: more than AG_TILEQ occupied tiles on the way
+            s_tileq[cnt++][tx] = (unsigned short)((unsigned)rc | link_bit);
+        };
+    };
+    // phase A, both links (no reconvergence point is needed between them: nothing lane-dependent is nested inside)
+    link_tiles(G, V, C, 0.0f, 0.0f, a.ex, a.ey, push_link(0u));
+    if (!hit) link_tiles(G, V, C, a.ex, a.ey, a.gx, a.gy, push_link(0x8000u));
+    if (!hit) drain();
+    return hit ? 1 : result;
 }
 
 // broad-phase selection: a compile-time choice for the rollout kernel (keeps its register
@@ -477,20 +517,25 @@ __device__ __forceinline__ int link_fast_hier(const GridDev &G, const GridView &
 enum { BP_ANY = 0, BP_LIST = 1, BP_TRAVERSAL = 2 };
 
 // 0 / 1 certain, 2 undecided
-template <int BP>
+template <int BP, typename GetArm>
 __device__ __forceinline__ int arm_fast(const GridDev &G, const GridView &V, const FastList *fl, const FastConst &C,
-                                        const ArmF &a) {
+                                        const ArmF &a, GetArm get_arm, double eps) {
     if (BP == BP_LIST) return (fl != nullptr && fl->m >= 0) ? arm_fast_list(fl, a, C) : 2;
     if (BP == BP_ANY && fl != nullptr && fl->m >= 0) return arm_fast_list(fl, a, C);
+    if (V.tiles != nullptr) {                                               // uniform over the launch
+        const unsigned lanes_h = __activemask();
+        const int vh = arm_fast_hier(G, V, C, a, get_arm, eps);
+        __syncwarp(lanes_h);
+        return vh;
+    }
     // The two traversals have lane-dependent trip counts.  Without an explicit reconvergence point between them
     // the lanes that finish link 1 first run ahead ALONE into link 2 (independent thread scheduling): ncu showed
     // link 2's row loop at 1.0 active thread per instruction (profiles/r1_c4_*).  Hence: no early return between
     // the links, and a __syncwarp over the lanes that entered together.
     const unsigned lanes = __activemask();
-    const bool hier = V.tiles != nullptr;                                   // uniform over the launch
-    const int v1 = hier ? link_fast_hier(G, V, C, 0.0f, 0.0f, a.ex, a.ey) : link_fast(G, V, C, 0.0f, 0.0f, a.ex, a.ey);
+    const int v1 = link_fast(G, V, C, 0.0f, 0.0f, a.ex, a.ey);
     __syncwarp(lanes);
-    const int v2 = (v1 == 1) ? 0 : (hier ? link_fast_hier(G, V, C, a.ex, a.ey, a.gx, a.gy) : link_fast(G, V, C, a.ex, a.ey, a.gx, a.gy));
+    const int v2 = (v1 == 1) ? 0 : link_fast(G, V, C, a.ex, a.ey, a.gx, a.gy);
     __syncwarp(lanes);
     return (v1 == 1 || v2 == 1) ? 1 : (v1 | v2);
 }
@@ -581,7 +626,7 @@ __device__ __forceinline__ int fast_decide(const ag_params &P, const GridDev &G,
                                            const double *tgt = nullptr) {
     bool ok;
     const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
-    const int c = ok ? arm_fast<BP>(G, V, fl, C, a) : 2;
+    const int c = ok ? arm_fast<BP>(G, V, fl, C, a, [&]() { return forward_kinematics(q1, q2, P.link_1, P.link_2); }, P.section_eps) : 2;
     int r = 0;
     double txd = P.target_x, tyd = P.target_y;
     if (want_reach) {
@@ -601,7 +646,7 @@ __device__ __forceinline__ bool fast_arm_collides(const ag_params &P, const Grid
     ArmF a;
     a.ex = (float)A.ex; a.ey = (float)A.ey; a.gx = (float)A.gx; a.gy = (float)A.gy;   // error 6e-8 < AG_DELTA_P
     const bool ok = fmax(fmax(fabs(A.ex), fabs(A.ey)), fmax(fabs(A.gx), fabs(A.gy))) < 1.0e3;
-    const int v = ok ? arm_fast<BP_ANY>(G, V, fl, C, a) : 2;
+    const int v = ok ? arm_fast<BP_ANY>(G, V, fl, C, a, [&]() { return A; }, P.section_eps) : 2;
     if (v != 2) return v == 1;
     int fh = 0;
     return arm_collides<AG_ENGINE_EXACT, false>(G, V, A, P.section_eps, fh, axis);

@@ -12,8 +12,8 @@ using namespace agd;
 // ag_rollout_lut.cu: the persistent kernel for scene_0-class grids (obstacle list, one grid, cartesian target)
 bool rollout_lut_applies(const ag_params &P, const GridDev &G, const RolloutDev &A);
 ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s);
-int64_t cspace_map_words(int32_t *b1, int32_t *b2);
-ag_status launch_cspace_map(const ag_params &P, const GridDev &G, uint32_t *map, cudaStream_t s);
+int64_t cspace_map_words(int32_t level, int32_t *b1, int32_t *b2);
+ag_status launch_cspace_map(const ag_params &P, const GridDev &G, int32_t level, uint32_t *map, cudaStream_t s);
 // ag_dense.cu: the warp-cooperative kernel for grids that go through the cell traversal (needs the transposed planes)
 bool rollout_coop_applies(const ag_params &P, const GridDev &G, const RolloutDev &A);
 ag_status launch_rollout_coop(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s);
@@ -717,8 +717,8 @@ ag_status make_grid_dev(const ag_params *p, const ag_grid *g, int64_t env_id0, i
         return AG_ERR_MODE;
     GridDev d;
     d.bits = g->bits; d.bits_t = g->bits_t; d.min_x = g->min_x; d.min_y = g->min_y;
-    d.hier = reinterpret_cast<const unsigned char *>(g->hier);
     d.T = (g->S + 7) / 8; d.cwpr = (d.T + 31) / 32;
+    d.hier = d.T <= AG_HIER_MAX_T ? reinterpret_cast<const unsigned char *>(g->hier) : nullptr;   // larger maps: the row walk
     d.hier_tiles_bytes = (int32_t)((((int64_t)d.T * d.T + 1) & ~(int64_t)1) * 8);
     d.hier_bytes = (int32_t)ag_grid_hier_bytes(g->S);
     d.side = g->side; d.half = g->env_size / 2.0; d.inv_side = 1.0 / g->side;
@@ -726,7 +726,7 @@ ag_status make_grid_dev(const ag_params *p, const ag_grid *g, int64_t env_id0, i
     d.S = g->S; d.wpr = g->words_per_row; d.n_grids = g->n_grids;
     d.stride_words = g->grid_stride_words; d.envs_per_grid = g->envs_per_grid;
     const int spad = (g->S + 1) & ~1;
-    const size_t bytes = 16 + (size_t)g->grid_stride_words * 4 * (g->bits_t ? 2 : 1) + (g->hier ? (size_t)d.hier_bytes : 0) +
+    const size_t bytes = 16 + (size_t)g->grid_stride_words * 4 * (g->bits_t ? 2 : 1) + (d.hier ? (size_t)d.hier_bytes : 0) +
                          (size_t)spad * 16;
     const bool uniform = g->n_grids == 1 || (g->envs_per_grid % AG_BLOCK == 0 && env_id0 % AG_BLOCK == 0);
     const bool aligned = ((uintptr_t)g->bits % 16 == 0) && ((uintptr_t)g->bits_t % 16 == 0) && ((uintptr_t)g->hier % 16 == 0) &&
@@ -1037,17 +1037,18 @@ ag_status ag_step_obs(const ag_params *p, const ag_grid *g, double *j1, double *
     return launched();
 }
 
-int64_t ag_cspace_map_words(int32_t *b1, int32_t *b2) { return cspace_map_words(b1, b2); }
+int64_t ag_cspace_map_words(int32_t level, int32_t *b1, int32_t *b2) { return cspace_map_words(level, b1, b2); }
 
-ag_status ag_cspace_map(const ag_params *p, const ag_grid *g, uint32_t *map, void *stream) {
+ag_status ag_cspace_map(const ag_params *p, const ag_grid *g, int32_t level, uint32_t *map, void *stream) {
     if (!p || !g || !map) return AG_ERR_NULL;
+    if (level < 0 || level > 1) return AG_ERR_MODE;
     if (g->n_grids != 1 || g->S > 32) return AG_ERR_SHAPE;
     if ((uintptr_t)map % 16) return AG_ERR_ALIGN;
     GridDev G;
     size_t smem;
     ag_status st = make_grid_dev(p, g, 0, AG_ENGINE_FAST, &G, &smem);
     if (st) return st;
-    return launch_cspace_map(*p, G, map, (cudaStream_t)stream);
+    return launch_cspace_map(*p, G, level, map, (cudaStream_t)stream);
 }
 
 ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream) {

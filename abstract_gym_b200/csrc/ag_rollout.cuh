@@ -9,6 +9,7 @@
 namespace agd {
 
 constexpr int AG_BLOCK = 256;
+static_assert(AG_BLOCK <= AG_TILEQ_COLS, "the tile queue of arm_fast_hier has one column per thread");
 
 struct RolloutDev {
     int64_t n, env_id0, row_stride;
