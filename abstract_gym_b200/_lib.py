@@ -87,8 +87,8 @@ SYMBOLS = {
     "ag_launch_count": (_i64, []),
     "ag_grid_hier_bytes": (_i64, [_i32]),
     "ag_grid_pack_hier": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp]),
-    "ag_cspace_map_words": (_i64, [_i32, C.POINTER(_i32), C.POINTER(_i32)]),
-    "ag_cspace_map": (_i32, [C.POINTER(Params), C.POINTER(Grid), _i32, _vp, _vp]),
+    "ag_cspace_map_words": (_i64, [C.POINTER(_i32), C.POINTER(_i32)]),
+    "ag_cspace_map": (_i32, [C.POINTER(Params), C.POINTER(Grid), _vp, _vp]),
     "ag_pipeline_create": (_i32, [C.POINTER(_vp), _i32, _i64, _i32, _i64, _i32, _i32, _i64]),
     "ag_pipeline_destroy": (None, [_vp]),
     "ag_rollout_host": (_i32, [_vp, C.POINTER(Params), C.POINTER(Grid), C.POINTER(RolloutArgs), _vp]),

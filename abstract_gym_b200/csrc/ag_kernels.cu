@@ -12,8 +12,8 @@ using namespace agd;
 // ag_rollout_lut.cu: the persistent kernel for scene_0-class grids (obstacle list, one grid, cartesian target)
 bool rollout_lut_applies(const ag_params &P, const GridDev &G, const RolloutDev &A);
 ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s);
-int64_t cspace_map_words(int32_t level, int32_t *b1, int32_t *b2);
-ag_status launch_cspace_map(const ag_params &P, const GridDev &G, int32_t level, uint32_t *map, cudaStream_t s);
+int64_t cspace_map_words(int32_t *b1, int32_t *b2);
+ag_status launch_cspace_map(const ag_params &P, const GridDev &G, uint32_t *map, cudaStream_t s);
 // ag_dense.cu: the warp-cooperative kernel for grids that go through the cell traversal (needs the transposed planes)
 bool rollout_coop_applies(const ag_params &P, const GridDev &G, const RolloutDev &A);
 ag_status launch_rollout_coop(const ag_params &P, const GridDev &G, const RolloutDev &A, size_t smem, cudaStream_t s);
@@ -1037,18 +1037,17 @@ ag_status ag_step_obs(const ag_params *p, const ag_grid *g, double *j1, double *
     return launched();
 }
 
-int64_t ag_cspace_map_words(int32_t level, int32_t *b1, int32_t *b2) { return cspace_map_words(level, b1, b2); }
+int64_t ag_cspace_map_words(int32_t *b1, int32_t *b2) { return cspace_map_words(b1, b2); }
 
-ag_status ag_cspace_map(const ag_params *p, const ag_grid *g, int32_t level, uint32_t *map, void *stream) {
+ag_status ag_cspace_map(const ag_params *p, const ag_grid *g, uint32_t *map, void *stream) {
     if (!p || !g || !map) return AG_ERR_NULL;
-    if (level < 0 || level > 1) return AG_ERR_MODE;
     if (g->n_grids != 1 || g->S > 32) return AG_ERR_SHAPE;
     if ((uintptr_t)map % 16) return AG_ERR_ALIGN;
     GridDev G;
     size_t smem;
     ag_status st = make_grid_dev(p, g, 0, AG_ENGINE_FAST, &G, &smem);
     if (st) return st;
-    return launch_cspace_map(*p, G, level, map, (cudaStream_t)stream);
+    return launch_cspace_map(*p, G, map, (cudaStream_t)stream);
 }
 
 ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream) {

@@ -1,35 +1,34 @@
 // ag_rollout_lut.cu -- K4 for scene_0-class grids (obstacle list, one grid, cartesian target): the rollout loop
-// experiment/experiment_0.py:20-34 fused over K steps, persistent warps, table-driven forward kinematics.
+// experiment/experiment_0.py:20-34 fused over K steps, persistent warps.  DESIGN.md "K4, scene_0 class".
 //
-// Why a second form of K4 (DESIGN.md "K4, scene_0 class"): the general kernel (ag_kernels.cu, k_rollout) is
-// instruction-issue-bound at ~236 warp-instructions per warp-step; ~145 of them are the float32 filter of an
-// uneventful step (99.6 % of all env-steps), and of those ~60 are the float32 sine / cosine of the two joints and
-// link 1's box test.  Here the float32 arm comes from two shared-memory tables indexed by the joint phase:
+// The general kernel (ag_kernels.cu, k_rollout) is instruction-issue-bound at ~236 warp-instructions per warp-step;
+// ~145 of them are the float32 filter of an uneventful step (99.5 % of all env-steps).  This kernel has two forms of a
+// much cheaper test for "this step is certainly uneventful"; both use the joint phase
 //
-//   x      = low word of fma(q, 2^32/2pi, 1.5*2^52)      one DFMA per joint: the turn fraction as a 32-bit integer
+//   x = low word of fma(q, 2^32/2pi, 1.5*2^52)            one DFMA per joint: the turn fraction as a 32-bit integer
+//
+// CMAP form (the default; scene-wide target): one bit of a configuration-space map in shared memory, indexed by the top
+//   bits of (x1, x2), says whether ANY pose of that bin can touch an obstacle or the target box -- no forward kinematics
+//   in the hot loop at all (k_cspace_build below explains how the map is made conservative, and how it is cached and
+//   validated against the current grid on the device at every launch).
+// table-arm form (per-env targets, or no map available): the float32 arm comes from two shared-memory tables,
 //   entry  = lut[x >> (32-B)]                            (c, s) * length at the bin centre, 8 bytes
 //   d      = (x mod 2^(32-B)) * 2pi/2^32 - pi/2^B        angle from the bin centre, one LOP3 + one FFMA
 //   point  = (1 - d*d/2) * (c, s) + d * (-s, c)          second-order Taylor step: FMUL + FFMA + FMUL2 + 2 FFMA
+//   With 2048 bins for link 1 and 512 for link 2, emulated op for op in numpy over 1.2e7 angles up to +-2^20 rad, the
+//   elbow is within 8.9e-8 m and the end effector within 2.1e-7 m of the float64 values: inside the error budget
+//   AG_DELTA_P = 3e-7 m the float32 filter of ag_fast.cuh was derived for.  Link 1 depends on joint_1 only: its test is
+//   one hazard bit per bin (hazard_interval), link 2 is a box test against the squares, the target a box pre-test.
 //
-// With 2048 bins for link 1 and 512 for link 2 the truncation error is below 2e-9 m / 2e-8 m; emulated op for op in
-// numpy over 1.2e7 angles up to +-2^20 rad the elbow is within 8.9e-8 m and link 2's half vector within 4.2e-8 m
-// of the float64 values, i.e. the end effector within 2.1e-7 m: inside the error budget AG_DELTA_P = 3e-7 m that
-// the float32 filter of ag_fast.cuh was derived for (its own polynomial arm measures 1.8e-7 m).  So the hot loop
-// runs the SAME decision as the general kernel's inner loop -- link-2 box test and reach pre-test with the same
-// thresholds -- on a cheaper arm.  Link 1 depends on joint_1 only: its test is folded into the table as one bit
-// per bin ("for some angle of this bin link 1 comes within 2e-6 m of a square"), computed exactly from the angular
-// interval each square subtends inside link 1's reach (hazard_interval).
-// A lane that clears all three tests is certainly uneventful; every other lane ("slow", ~0.5 % of env-steps) goes
-// through the float32 narrow phase, the float64 filter and the reference arithmetic exactly as in the general
-// kernel (slow_step).  Results are therefore identical to the general kernel's and the reference's;
-// tests/test_gpu_parity.py runs both.
+// A lane that clears the test is certainly uneventful; every other lane ("slow", ~0.5 % of env-steps) goes through the
+// float32 narrow phase, the float64 filter and the reference arithmetic exactly as in the general kernel (level 1 in the
+// loop, level 2 = settle_step).  Results are therefore identical to the general kernel's and the reference's;
+// tests/test_gpu_parity.py runs all forms.
 //
-// Structure: a persistent grid (one 256-thread block per SM slot); the block builds the tables once, every warp
-// then walks 32-env tiles (tile = warp index + i * #warps).  Per tile: state -> registers, the next valid reset
-// pose is drawn up front by all 32 lanes together (draw_valid_pose; consumed on collision, so an episode end costs
-// a few dozen instructions instead of a one-lane rejection loop), then K steps of
-//   action (register prefetch three rows ahead) -> 2 DADD -> table arm -> box test / reach pre-test ->
-//   record (2 F2F + 2 STG) -> vote.
+// Structure: a persistent grid (256-thread blocks, 2 per SM); every warp draws 32-env tiles from a global counter.
+// Per tile: state -> registers, the next valid reset pose is drawn up front by all 32 lanes together (draw_valid_pose;
+// consumed on collision), then K steps of
+//   action (cp.async ring, RING - 1 rows ahead) -> 2 DADD -> test -> record (2 F2F + 2 STG) -> vote.
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -63,12 +62,6 @@ namespace {
 constexpr int CB1 = AG_CMAP_B1, CB2 = AG_CMAP_B2;
 static_assert(CB1 >= 6 && CB2 >= 6 && CB1 + CB2 <= 20, "the map must fit shared memory");
 constexpr int CMAP_WORDS = 1 << (CB1 + CB2 - 5);
-// second level, in global memory (L2 / L1): every bin split 4 x 4.  Consulted by a slow lane before it computes anything
-// (level 1 of the slow path): three of four false alarms of the shared-memory map end there.
-constexpr int FB1 = CB1 + 2, FB2 = CB2 + 2;
-constexpr int FMAP_WORDS = 1 << (FB1 + FB2 - 5);
-constexpr int CMAP_CW_PER_BLOCK = 8;                     // k_cspace_build: coarse words per 256-thread block
-constexpr int CMAP_BUF_WORDS = 64 + CMAP_WORDS + FMAP_WORDS;
 constexpr int CMAP_HDR_WORDS = 64;                       // 256-byte header in front of the map words
 constexpr int CMAP_SLOTS = 16;
 struct CmapHeader {
@@ -86,7 +79,7 @@ constexpr int LB = 256, LW = LB / 32;
 // gives all in-flight LDGs of the loop ONE scoreboard slot, so a consumer waits for every outstanding load and the
 // effective distance is a single step: profiles/r2b.)
 #ifndef AG_LUT_RING
-#define AG_LUT_RING 4
+#define AG_LUT_RING 8
 #endif
 constexpr int RING = AG_LUT_RING;
 static_assert((RING & (RING - 1)) == 0 && RING >= 4, "ring slots: a power of two");
@@ -106,7 +99,6 @@ struct LutConst {
     uint32_t slot;          // this launch's pair of tile / done counters (g_tile_sched)
     uint32_t cmap_off;      // CMAP: byte offset of the map's shared-memory copy in the dynamic segment
     const uint32_t *cmap;   // CMAP: the map words in global memory (k_cspace_build)
-    const uint32_t *fmap;   // CMAP: the second-level map (global memory), consulted by level 1 of the slow path
 };
 
 // Dynamic tile scheduling: warps draw 32-env tiles from a device-global counter, so no warp idles while tiles remain
@@ -357,7 +349,7 @@ __device__ void fill_table(float2 *lut, int n, double len, const float *hz, int 
 // buffer that is reused between launches: every launch re-derives a 64-bit key from the CURRENT grid words and
 // parameters on the device (thread 0 of each block, ~100 words) and rebuilds the map only when the stored key differs.
 constexpr double CMAP_MG = 2.0e-6;
-constexpr int CMAP_BUILD_BLOCKS = CMAP_WORDS / CMAP_CW_PER_BLOCK;
+constexpr int CMAP_BUILD_BLOCKS = 128;
 constexpr uint32_t CMAP_VERSION = 1;
 
 struct V2 { double x, y; };
@@ -381,71 +373,6 @@ __device__ __forceinline__ double axis_gap(V2 n, const V2 (&P)[NP], V2 c, double
     return fmax(lo - (cc + r), (cc - r) - hi);
 }
 
-// Is bin (b1, b2) of a 2^B1 x 2^B2 map a hazard?  sq: the occupied squares (float64 corners), hz: link 1's angular intervals
-template <int B1, int B2>
-__device__ bool bin_hazard(const ag_params &P, int b1, int b2, int m, const double (*s_sq)[4], const float *s_hz) {
-    constexpr int N1 = 1 << B1, N2 = 1 << B2;
-    const double l1 = P.link_1, l2 = P.link_2;
-    double sd, cd;
-    sincospi(1.0 / (double)N1, &sd, &cd);
-    const double sag1 = l1 * (1.0 - cd);
-    sincospi(1.0 / (double)N2, &sd, &cd);
-    const double sag2 = l2 * (1.0 - cd);
-    const double infl = sag1 + sag2 + CMAP_MG;
-    const float hw1 = (float)(TWO_PI / (double)(2 * N1)) + 2.0e-6f;              // half a bin of joint_1 + rounding
-    bool haz = m < 0;
-    // ---- link 1: exact angular intervals
-    const float th1 = ((float)b1 + 0.5f) * (float)(TWO_PI / (double)N1);
-    for (int k = 0; k < m; ++k) {
-        float dlt = th1 - s_hz[2 * k];
-        dlt -= (float)TWO_PI * rintf(dlt * (float)(1.0 / TWO_PI));
-        if (fabsf(dlt) <= s_hz[2 * k + 1] + hw1) haz = true;
-    }
-    // ---- link 2: the swept polygon against every square
-    V2 Ea, Eb, Ec, Ua, Ub, Uc;
-    sincospi(2.0 * (double)b1 / (double)N1, &Ea.y, &Ea.x);
-    sincospi(2.0 * (double)(b1 + 1) / (double)N1, &Eb.y, &Eb.x);
-    sincospi((2.0 * (double)b1 + 1.0) / (double)N1, &Ec.y, &Ec.x);
-    sincospi(2.0 * (double)b2 / (double)N2, &Ua.y, &Ua.x);
-    sincospi(2.0 * (double)(b2 + 1) / (double)N2, &Ub.y, &Ub.x);
-    sincospi((2.0 * (double)b2 + 1.0) / (double)N2, &Uc.y, &Uc.x);
-    const V2 n1c = {Ec.x, Ec.y};                                          // normal of the elbow chord = link 1's direction
-    const V2 n2a = {-Ua.y, Ua.x}, n2b = {-Ub.y, Ub.x}, n2c = {-Uc.y, Uc.x};   // link 2's normals at the bin's edges / centre
-    const V2 ea = {l1 * Ea.x, l1 * Ea.y}, eb = {l1 * Eb.x, l1 * Eb.y}, ec = {l1 * Ec.x, l1 * Ec.y};
-    const V2 ua = {l2 * Ua.x, l2 * Ua.y}, ub = {l2 * Ub.x, l2 * Ub.y};
-    const V2 gc = {ec.x + l2 * Uc.x, ec.y + l2 * Uc.y};
-    const V2 poly[6] = {ea, eb, {ea.x + ua.x, ea.y + ua.y}, {ea.x + ub.x, ea.y + ub.y},
-                        {eb.x + ua.x, eb.y + ua.y}, {eb.x + ub.x, eb.y + ub.y}};
-    for (int k = 0; k < m && !haz; ++k) {
-        const V2 c = {0.5 * (s_sq[k][0] + s_sq[k][2]), 0.5 * (s_sq[k][1] + s_sq[k][3])};
-        const double hx = 0.5 * (s_sq[k][2] - s_sq[k][0]), hy = 0.5 * (s_sq[k][3] - s_sq[k][1]);
-        double gap = axis_gap(V2{1.0, 0.0}, poly, c, hx, hy);
-        gap = fmax(gap, axis_gap(V2{0.0, 1.0}, poly, c, hx, hy));
-        gap = fmax(gap, axis_gap(n2c, poly, c, hx, hy));
-        gap = fmax(gap, axis_gap(n2a, poly, c, hx, hy));
-        gap = fmax(gap, axis_gap(n2b, poly, c, hx, hy));
-        gap = fmax(gap, axis_gap(n1c, poly, c, hx, hy));
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) {                                     // corner -> centre pose's end effector / elbow
-            const double qx = (j & 1) ? s_sq[k][2] : s_sq[k][0], qy = (j & 2) ? s_sq[k][3] : s_sq[k][1];
-            const V2 from = (j & 4) ? ec : gc;
-            const double vx = from.x - qx, vy = from.y - qy, nv = sqrt(vx * vx + vy * vy);
-            if (nv > 1.0e-9) gap = fmax(gap, axis_gap(V2{vx / nv, vy / nv}, poly, c, hx, hy) * (1.0 - 1.0e-12));
-        }
-        if (!(gap > infl)) haz = true;
-    }
-    // ---- the target box (scene_0.py:129-130) against the box of the swept end effector
-    {
-        const double gx0 = fmin(fmin(poly[2].x, poly[3].x), fmin(poly[4].x, poly[5].x)) - infl;
-        const double gx1 = fmax(fmax(poly[2].x, poly[3].x), fmax(poly[4].x, poly[5].x)) + infl;
-        const double gy0 = fmin(fmin(poly[2].y, poly[3].y), fmin(poly[4].y, poly[5].y)) - infl;
-        const double gy1 = fmax(fmax(poly[2].y, poly[3].y), fmax(poly[4].y, poly[5].y)) + infl;
-        const double e = fabs(P.reach_eps);
-        if (!(gx0 > P.target_x + e || gx1 < P.target_x - e || gy0 > P.target_y + e || gy1 < P.target_y - e)) haz = true;
-    }
-    return haz;
-}
-
 __global__ void __launch_bounds__(256)
 k_cspace_build(const __grid_constant__ ag_params P, const __grid_constant__ GridDev G, uint32_t *buf, uint32_t slot) {
     __shared__ unsigned long long s_key;
@@ -455,7 +382,7 @@ k_cspace_build(const __grid_constant__ ag_params P, const __grid_constant__ Grid
     CmapHeader *H = reinterpret_cast<CmapHeader *>(buf);
     if (threadIdx.x == 0) {
         unsigned long long h = 0xCBF29CE484222325ull;
-        h = mix64(h, ((unsigned long long)(CMAP_VERSION + 1) << 48) | ((unsigned long long)CB1 << 40) | ((unsigned long long)CB2 << 32) | (unsigned)G.S);
+        h = mix64(h, ((unsigned long long)CMAP_VERSION << 48) | ((unsigned long long)CB1 << 40) | ((unsigned long long)CB2 << 32) | (unsigned)G.S);
         const double par[6] = {P.link_1, P.link_2, P.target_x, P.target_y, P.reach_eps, G.side};
         for (int i = 0; i < 6; ++i) h = mix64(h, (unsigned long long)__double_as_longlong(par[i]));
         int m = 0;
@@ -489,24 +416,69 @@ k_cspace_build(const __grid_constant__ ag_params P, const __grid_constant__ Grid
             hazard_interval(s_sq[threadIdx.x][0] - CMAP_MG, s_sq[threadIdx.x][1] - CMAP_MG, s_sq[threadIdx.x][2] + CMAP_MG,
                             s_sq[threadIdx.x][3] + CMAP_MG, P.link_1, s_hz[2 * threadIdx.x], s_hz[2 * threadIdx.x + 1]);
         __syncthreads();
-        // ---- coarse level: this block's CMAP_CW_PER_BLOCK words = 256 bins, one per thread (a warp = one word)
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int cw = blockIdx.x * CMAP_CW_PER_BLOCK + warp;                    // coarse word: 32 bins of joint_2 at one joint_1
-        const int cb1 = cw >> (CB2 - 5), cw2 = cw & ((1 << (CB2 - 5)) - 1);
-        const bool chaz = bin_hazard<CB1, CB2>(P, cb1, cw2 * 32 + lane, m, s_sq, s_hz);
-        const uint32_t cword = __ballot_sync(0xFFFFFFFFu, chaz);
-        if (lane == 0) buf[CMAP_HDR_WORDS + cw] = cword;
-        // ---- fine level: the 4 x 4 children of every coarse bin; children of a CLEAR bin are never looked at (written 0).
-        // One coarse word has 4 fine rows x 4 fine words below it; the warp that made the coarse word makes them.
-        uint32_t *fine = buf + CMAP_HDR_WORDS + CMAP_WORDS;
+        constexpr int N1c = 1 << CB1, N2c = 1 << CB2;
+        const double l1 = P.link_1, l2 = P.link_2;
+        double sd, cd;
+        sincospi(1.0 / (double)N1c, &sd, &cd);
+        const double sag1 = l1 * (1.0 - cd);
+        sincospi(1.0 / (double)N2c, &sd, &cd);
+        const double sag2 = l2 * (1.0 - cd);
+        const double infl = sag1 + sag2 + CMAP_MG;
+        const float hw1 = (float)(TWO_PI / (double)(2 * N1c)) + 2.0e-6f;          // half a bin of joint_1 + rounding
+        for (int bin = blockIdx.x * 256 + threadIdx.x; bin < N1c * N2c; bin += gridDim.x * 256) {   // a warp = 32 bins of joint_2
+            const int b1 = bin >> CB2, b2 = bin & (N2c - 1);
+            bool haz = m < 0;
+            // ---- link 1: exact angular intervals
+            const float th1 = ((float)b1 + 0.5f) * (float)(TWO_PI / (double)N1c);
+            for (int k = 0; k < m; ++k) {
+                float dlt = th1 - s_hz[2 * k];
+                dlt -= (float)TWO_PI * rintf(dlt * (float)(1.0 / TWO_PI));
+                if (fabsf(dlt) <= s_hz[2 * k + 1] + hw1) haz = true;
+            }
+            // ---- link 2: the swept polygon against every square
+            V2 Ea, Eb, Ec, Ua, Ub, Uc;
+            sincospi(2.0 * (double)b1 / (double)N1c, &Ea.y, &Ea.x);
+            sincospi(2.0 * (double)(b1 + 1) / (double)N1c, &Eb.y, &Eb.x);
+            sincospi((2.0 * (double)b1 + 1.0) / (double)N1c, &Ec.y, &Ec.x);
+            sincospi(2.0 * (double)b2 / (double)N2c, &Ua.y, &Ua.x);
+            sincospi(2.0 * (double)(b2 + 1) / (double)N2c, &Ub.y, &Ub.x);
+            sincospi((2.0 * (double)b2 + 1.0) / (double)N2c, &Uc.y, &Uc.x);
+            const V2 n1c = {Ec.x, Ec.y};                                          // normal of the elbow chord = link 1's direction
+            const V2 n2a = {-Ua.y, Ua.x}, n2b = {-Ub.y, Ub.x}, n2c = {-Uc.y, Uc.x};   // link 2's normals at the bin's edges / centre
+            const V2 ea = {l1 * Ea.x, l1 * Ea.y}, eb = {l1 * Eb.x, l1 * Eb.y}, ec = {l1 * Ec.x, l1 * Ec.y};
+            const V2 ua = {l2 * Ua.x, l2 * Ua.y}, ub = {l2 * Ub.x, l2 * Ub.y};
+            const V2 gc = {ec.x + l2 * Uc.x, ec.y + l2 * Uc.y};
+            const V2 poly[6] = {ea, eb, {ea.x + ua.x, ea.y + ua.y}, {ea.x + ub.x, ea.y + ub.y},
+                                {eb.x + ua.x, eb.y + ua.y}, {eb.x + ub.x, eb.y + ub.y}};
+            for (int k = 0; k < m && !haz; ++k) {
+                const V2 c = {0.5 * (s_sq[k][0] + s_sq[k][2]), 0.5 * (s_sq[k][1] + s_sq[k][3])};
+                const double hx = 0.5 * (s_sq[k][2] - s_sq[k][0]), hy = 0.5 * (s_sq[k][3] - s_sq[k][1]);
+                double gap = axis_gap(V2{1.0, 0.0}, poly, c, hx, hy);
+                gap = fmax(gap, axis_gap(V2{0.0, 1.0}, poly, c, hx, hy));
+                gap = fmax(gap, axis_gap(n2c, poly, c, hx, hy));
+                gap = fmax(gap, axis_gap(n2a, poly, c, hx, hy));
+                gap = fmax(gap, axis_gap(n2b, poly, c, hx, hy));
+                gap = fmax(gap, axis_gap(n1c, poly, c, hx, hy));
 #pragma unroll 1
-        for (int ij = 0; ij < 16; ++ij) {
-            const int i = ij >> 2, j = ij & 3;
-            const int fb1 = cb1 * 4 + i, fw2 = cw2 * 4 + j;                       // fine row, fine word within the row
-            const bool parent = (cword >> (8 * j + (lane >> 2))) & 1u;
-            const bool fhaz = parent && bin_hazard<FB1, FB2>(P, fb1, fw2 * 32 + lane, m, s_sq, s_hz);
-            const uint32_t fword = __ballot_sync(0xFFFFFFFFu, fhaz);
-            if (lane == 0) fine[(fb1 << (FB2 - 5)) + fw2] = fword;
+                for (int j = 0; j < 8; ++j) {                                     // corner -> centre pose's end effector / elbow
+                    const double qx = (j & 1) ? s_sq[k][2] : s_sq[k][0], qy = (j & 2) ? s_sq[k][3] : s_sq[k][1];
+                    const V2 from = (j & 4) ? ec : gc;
+                    const double vx = from.x - qx, vy = from.y - qy, nv = sqrt(vx * vx + vy * vy);
+                    if (nv > 1.0e-9) gap = fmax(gap, axis_gap(V2{vx / nv, vy / nv}, poly, c, hx, hy) * (1.0 - 1.0e-12));
+                }
+                if (!(gap > infl)) haz = true;
+            }
+            // ---- the target box (scene_0.py:129-130) against the box of the swept end effector
+            {
+                const double gx0 = fmin(fmin(poly[2].x, poly[3].x), fmin(poly[4].x, poly[5].x)) - infl;
+                const double gx1 = fmax(fmax(poly[2].x, poly[3].x), fmax(poly[4].x, poly[5].x)) + infl;
+                const double gy0 = fmin(fmin(poly[2].y, poly[3].y), fmin(poly[4].y, poly[5].y)) - infl;
+                const double gy1 = fmax(fmax(poly[2].y, poly[3].y), fmax(poly[4].y, poly[5].y)) + infl;
+                const double e = fabs(P.reach_eps);
+                if (!(gx0 > P.target_x + e || gx1 < P.target_x - e || gy0 > P.target_y + e || gy1 < P.target_y - e)) haz = true;
+            }
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, haz);
+            if ((threadIdx.x & 31) == 0) buf[CMAP_HDR_WORDS + (bin >> 5)] = word;
         }
     }
     // the last block of this launch publishes the key (blocks that skipped count too: the map they saw was complete)
@@ -551,7 +523,7 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
               const __grid_constant__ RolloutDev A, const __grid_constant__ LutConst L) {
     extern __shared__ __align__(16) unsigned char smem_grid[];  // the staged grid (layout of stage_grid), then SlowShared
     __shared__ __align__(16) float2 s_lut1[CMAP ? 1 : N1], s_lut2[CMAP ? 1 : N2];
-    __shared__ __align__(16) float2 s_ring[LW][RING][32];   // action rows t .. t+3 of each warp's tile (cp.async)
+    __shared__ __align__(16) float2 s_ring[LW][RING][32];   // action rows t .. t+RING-1 of each warp's tile (cp.async)
     __shared__ FastList s_fl;
     __shared__ float s_hz[2 * AG_LIST_MAX];
     __shared__ unsigned long long s_acc[AG_ST_COUNT + AG_DIAG_COUNT];
@@ -772,24 +744,12 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
             event = false;
             if (slow && active) {
                 int c = 2, r = 2;
-                if (CMAP) {
-                    // first the second-level map (4 x 4 finer, global memory): a CLEAR bit there ends the matter
-                    bool look = true;
-                    if (l_inr && thr < INF) {
-                        const uint32_t x1 = (uint32_t)__double2loint(fma(q1, L.phase_scale, PHASE_MAGIC));
-                        const uint32_t x2 = (uint32_t)__double2loint(fma(q2, L.phase_scale, PHASE_MAGIC));
-                        const uint32_t fb = ((x1 >> (32 - FB1)) << FB2) | (x2 >> (32 - FB2));
-                        look = ((__ldg(L.fmap + (fb >> 5)) >> (fb & 31u)) & 1u) != 0;
-                    }
-                    if (!look) {
-                        c = 0; r = 0;
-                    } else {                                                     // the hot loop had no arm: float32 FK now
-                        bool ok;
-                        const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
-                        if (ok) {
-                            c = s_fl.m < 0 ? 2 : arm_fast_list(&s_fl, a, C, true);
-                            r = reach_fast_at(C, a, tx, ty);
-                        }
+                if (CMAP) {                                                      // the hot loop had no arm: float32 FK now
+                    bool ok;
+                    const ArmF a = fast_forward_kinematics(q1, q2, C, ok);
+                    if (ok) {
+                        c = s_fl.m < 0 ? 2 : arm_fast_list(&s_fl, a, C, true);
+                        r = reach_fast_at(C, a, tx, ty);
                     }
                 } else if (l_inr) {
                     ArmF a;
@@ -960,7 +920,7 @@ uint32_t *cmap_buffer(const ag_params &P, const GridDev &G, cudaStream_t s) {
             cudaDeviceSynchronize();
             if (lru->dev != cur) { cudaFree(lru->buf); lru->buf = nullptr; cudaSetDevice(cur); }
         }
-        if (lru->buf == nullptr && cudaMalloc(&lru->buf, (size_t)CMAP_BUF_WORDS * 4) != cudaSuccess) {
+        if (lru->buf == nullptr && cudaMalloc(&lru->buf, (size_t)(CMAP_HDR_WORDS + CMAP_WORDS) * 4) != cudaSuccess) {
             cudaGetLastError();
             lru->buf = nullptr; lru->dev = -1;
             return nullptr;
@@ -975,16 +935,16 @@ uint32_t *cmap_buffer(const ag_params &P, const GridDev &G, cudaStream_t s) {
 }
 }  // namespace
 
-int64_t cspace_map_words(int32_t level, int32_t *b1, int32_t *b2) {
-    if (b1) *b1 = level ? FB1 : CB1;
-    if (b2) *b2 = level ? FB2 : CB2;
-    return level ? FMAP_WORDS : CMAP_WORDS;
+int64_t cspace_map_words(int32_t *b1, int32_t *b2) {
+    if (b1) *b1 = CB1;
+    if (b2) *b2 = CB2;
+    return CMAP_WORDS;
 }
 
 // the map alone, into a caller's buffer (ag_cspace_map): built in a scratch buffer with the header in front
-ag_status launch_cspace_map(const ag_params &P, const GridDev &G, int32_t level, uint32_t *map, cudaStream_t s) {
+ag_status launch_cspace_map(const ag_params &P, const GridDev &G, uint32_t *map, cudaStream_t s) {
     uint32_t *buf = nullptr;
-    cudaError_t e = cudaMallocAsync(&buf, (size_t)CMAP_BUF_WORDS * 4, s);
+    cudaError_t e = cudaMallocAsync(&buf, (size_t)(CMAP_HDR_WORDS + CMAP_WORDS) * 4, s);
     if (e != cudaSuccess) return (ag_status)e;
     e = cudaMemsetAsync(buf, 0, CMAP_HDR_WORDS * 4, s);
     if (e == cudaSuccess) {
@@ -992,9 +952,7 @@ ag_status launch_cspace_map(const ag_params &P, const GridDev &G, int32_t level,
         ag_note_launch();
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(map, buf + CMAP_HDR_WORDS + (level ? CMAP_WORDS : 0), (size_t)(level ? FMAP_WORDS : CMAP_WORDS) * 4,
-                            cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(map, buf + CMAP_HDR_WORDS, (size_t)CMAP_WORDS * 4, cudaMemcpyDeviceToDevice, s);
     cudaFreeAsync(buf, s);
     return (ag_status)e;
 }
@@ -1013,7 +971,7 @@ ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const Rollout
     const bool m3 = A.max_occupied >= 0 && A.max_occupied <= 3;
     // The map form: scene-wide target only (the map holds the target box), |link| small enough for the build's margins
     static const bool no_cmap = std::getenv("AG_ROLLOUT_NO_CMAP") != nullptr;
-    L.cmap = nullptr; L.fmap = nullptr; L.cmap_off = 0;
+    L.cmap = nullptr; L.cmap_off = 0;
     if (!no_cmap && A.targets == nullptr) {
         uint32_t *buf = cmap_buffer(P, G, s);
         if (buf != nullptr) {
@@ -1023,7 +981,6 @@ ag_status launch_rollout_lut(const ag_params &P, const GridDev &G, const Rollout
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return (ag_status)e;
             L.cmap = buf + CMAP_HDR_WORDS;
-            L.fmap = buf + CMAP_HDR_WORDS + CMAP_WORDS;
             L.cmap_off = (uint32_t)((smem + 15) & ~(size_t)15);
             smem = (size_t)L.cmap_off + (size_t)CMAP_WORDS * 4;
         }

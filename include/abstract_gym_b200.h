@@ -256,18 +256,16 @@ typedef struct ag_rollout_args {
 
 AG_API ag_status ag_rollout(const ag_params *p, const ag_grid *g, const ag_rollout_args *a, void *stream);
 
-/* The configuration-space maps ag_rollout consults for scene_0-class grids (one staged grid of at most 8 occupied
+/* The configuration-space map ag_rollout consults for scene_0-class grids (one staged grid of at most 8 occupied
  * cells, S <= 32, FAST engine, scene-wide cartesian target): one bit per bin of (joint_1, joint_2) mod 2 pi,
- * 2^*b1 x 2^*b2 bins; bit i = (i1 << *b2 | i2) is bit (i & 31) of word i >> 5.  CLEAR means: for every pose of the bin,
+ * 2^*b1 x 2^*b2 bins; bit (i1 << *b2 | i2) is bit (i & 31) of word i >> 5.  CLEAR means: for every pose of the bin,
  * Scene.collision_check() is False and check_target_reached() is False (scenario/scene_0.py:60-76,129-130), so a step
- * that lands there is uneventful; SET means "evaluate".  Level 0 is the map the kernel's hot loop reads from shared
- * memory; level 1 splits every bin 4 x 4 (children of CLEAR level-0 bins are left 0: they are never consulted) and is
- * read from global memory by lanes whose level-0 bit is set.  ag_rollout builds and caches both itself (validated
- * against the current grid and parameters at every launch); this entry point builds them into a caller's device
- * buffer of ag_cspace_map_words(level) uint32 words -- it exists for inspection and for tests/test_gpu_parity.py,
- * which checks the CLEAR guarantee against the BRUTE engine. */
-AG_API int64_t ag_cspace_map_words(int32_t level, int32_t *b1, int32_t *b2);
-AG_API ag_status ag_cspace_map(const ag_params *p, const ag_grid *g, int32_t level, uint32_t *map, void *stream);
+ * that lands there is uneventful; SET means "evaluate".  ag_rollout builds and caches the map itself (validated against
+ * the current grid and parameters at every launch); this entry point builds it into a caller's device buffer of
+ * ag_cspace_map_words() uint32 words -- it exists for inspection and for tests/test_gpu_parity.py, which checks the
+ * CLEAR guarantee against the BRUTE engine. */
+AG_API int64_t ag_cspace_map_words(int32_t *b1, int32_t *b2);
+AG_API ag_status ag_cspace_map(const ag_params *p, const ag_grid *g, uint32_t *map, void *stream);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 AG_API int64_t ag_launch_count(void);

@@ -1268,13 +1268,9 @@ def test_cspace_map_clear_bins_are_uneventful(ag, torch_, case):
     torch = torch_
     lib = _lib.load()
     b1, b2 = C.c_int32(), C.c_int32()
-    words = lib.ag_cspace_map_words(0, C.byref(b1), C.byref(b2))
+    words = lib.ag_cspace_map_words(C.byref(b1), C.byref(b2))
     b1, b2 = b1.value, b2.value
     assert words * 32 == 1 << (b1 + b2)
-    f1, f2 = C.c_int32(), C.c_int32()
-    fwords = lib.ag_cspace_map_words(1, C.byref(f1), C.byref(f2))
-    f1, f2 = f1.value, f2.value
-    assert (f1, f2) == (b1 + 2, b2 + 2) and fwords * 32 == 1 << (f1 + f2)
     rng = np.random.default_rng(21)
     link = (0.4, 0.3)
     if case == "scene0":
@@ -1298,9 +1294,7 @@ def test_cspace_map_clear_bins_are_uneventful(ag, torch_, case):
     kw = {} if target is None else dict(target_c=ag.Point(*target))
     sc = ag.BatchedScene(robot, grid, engine="brute", **kw)
     m = torch.zeros(words, dtype=torch.int32, device="cuda")
-    _lib.check(lib.ag_cspace_map(sc.params(), sc.grid.c_struct(), 0, ptr(m), stream_ptr(sc.device)), "ag_cspace_map")
-    mf = torch.zeros(fwords, dtype=torch.int32, device="cuda")
-    _lib.check(lib.ag_cspace_map(sc.params(), sc.grid.c_struct(), 1, ptr(mf), stream_ptr(sc.device)), "ag_cspace_map")
+    _lib.check(lib.ag_cspace_map(sc.params(), sc.grid.c_struct(), ptr(m), stream_ptr(sc.device)), "ag_cspace_map")
     eventful = (sc.collision_check() | sc.check_target_reached()).cpu().numpy()
     mw = m.cpu().numpy().view(np.uint32)
     # the kernel's phase: low 32 bits of round(q * 2^32 / 2pi); numpy's product rounds twice (fma does not), which moves
@@ -1312,18 +1306,10 @@ def test_cspace_map_clear_bins_are_uneventful(ag, torch_, case):
     is_set = ((mw[bit >> 5] >> (bit & 31).astype(np.uint32)) & 1).astype(bool)
     bad = eventful & ~is_set
     assert not bad.any(), "%d eventful poses in CLEAR bins, e.g. q = (%r, %r)" % (bad.sum(), q1[bad][0], q2[bad][0])
-    # level 1: consulted only under a SET level-0 bit
-    mfw = mf.cpu().numpy().view(np.uint32)
-    fbit = ((x1 >> (32 - f1)) << f2) | (x2 >> (32 - f2))
-    f_set = ((mfw[fbit >> 5] >> (fbit & 31).astype(np.uint32)) & 1).astype(bool)
-    assert not (f_set & ~is_set).any(), "level-1 bits under CLEAR level-0 bins must stay 0"
-    bad1 = eventful & ~f_set
-    assert not bad1.any(), "%d eventful poses in CLEAR level-1 bins, e.g. q = (%r, %r)" % (bad1.sum(), q1[bad1][0], q2[bad1][0])
     uni = slice(k + e, n)
     frac = (is_set[uni] & ~eventful[uni]).sum() / max((~eventful[uni]).sum(), 1)
-    frac1 = (f_set[uni] & ~eventful[uni]).sum() / max((~eventful[uni]).sum(), 1)
-    print("cspace map %s: %d x %d bins, %.2f %% of them set; %.3f %% of the uneventful uniform poses sit in SET bins, "
-          "%.3f %% after level 1 (%d x %d)" % (case, 1 << b1, 1 << b2, 100 * is_set[uni].mean(), 100 * frac, 100 * frac1, 1 << f1, 1 << f2))
+    print("cspace map %s: %d x %d bins, %.2f %% of them set; %.3f %% of the uneventful uniform poses sit in SET bins"
+          % (case, 1 << b1, 1 << b2, 100 * is_set[uni].mean(), 100 * frac))
     assert frac < 0.03
     assert eventful.sum() > 1000
 
