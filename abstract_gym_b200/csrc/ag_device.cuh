@@ -30,7 +30,8 @@ struct GridDev {
     int64_t stride_words;
     int64_t envs_per_grid;
     int32_t T, cwpr;          // hier: tiles per side, summary words per row
-    int32_t hier_tiles_bytes; // hier: bytes of the tile array (the summary bitmap follows it)
+    int32_t hier_tiles_bytes; // hier: bytes of the tile array (the two summary bitmaps follow it)
+    int32_t hier_coarse_words;// hier: words of one summary bitmap (row-major, then column-major)
     int32_t hier_bytes;       // hier: bytes per grid
 };
 
@@ -41,11 +42,13 @@ struct GridView {
     const double *min_x;
     const double *min_y;
     const unsigned long long *tiles;   // two-level form: 8x8 tiles, T*T of them; nullptr = none
-    const uint32_t *coarse;            // ... and the T x T summary bitmap
+    const uint32_t *coarse;            // ... and the T x T summary bitmap (lines = tile rows)
+    const uint32_t *coarse_t;          // ... transposed (lines = tile columns)
 };
 __device__ __forceinline__ void view_hier(GridView &V, const GridDev &G, const unsigned char *h) {
     V.tiles = reinterpret_cast<const unsigned long long *>(h);
     V.coarse = h ? reinterpret_cast<const uint32_t *>(h + G.hier_tiles_bytes) : nullptr;
+    V.coarse_t = h ? V.coarse + G.hier_coarse_words : nullptr;
 }
 
 __device__ __forceinline__ int64_t grid_of_env(const GridDev &G, int64_t gid) {

@@ -49,7 +49,7 @@ int64_t ag_grid_stride_words(int32_t S) {
 
 int64_t ag_grid_hier_bytes(int32_t S) {
     const int64_t T = (S + 7) / 8, cw = (T + 31) / 32;
-    return ((T * T + 1) & ~(int64_t)1) * 8 + ((T * cw + 3) & ~(int64_t)3) * 4;
+    return ((T * T + 1) & ~(int64_t)1) * 8 + 2 * ((T * cw + 3) & ~(int64_t)3) * 4;     // tiles, summary rows, summary columns
 }
 
 ag_status ag_grid_pack_host(const uint8_t *occ, int32_t rows, int32_t cols, uint32_t *bits_out) {

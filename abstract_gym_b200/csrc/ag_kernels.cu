@@ -43,7 +43,8 @@ __global__ void k_grid_pack(const uint8_t *__restrict__ occ, int S, int wpr, int
 
 // bits -> the two-level form (ag_grid.hier): one thread per 8x8 tile; the summary bitmap is zeroed by the launcher
 __global__ void k_grid_pack_hier(const uint32_t *__restrict__ bits, int S, int wpr, int n_grids, int64_t stride_words,
-                                 unsigned char *__restrict__ hier, int T, int cwpr, int64_t tiles_bytes, int64_t hier_bytes) {
+                                 unsigned char *__restrict__ hier, int T, int cwpr, int64_t tiles_bytes, int64_t coarse_words,
+                                 int64_t hier_bytes) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)T * T * n_grids) return;
     const int64_t g = i / ((int64_t)T * T);
@@ -58,7 +59,11 @@ __global__ void k_grid_pack_hier(const uint32_t *__restrict__ bits, int S, int w
     }
     unsigned char *gh = hier + g * hier_bytes;
     reinterpret_cast<unsigned long long *>(gh)[(int64_t)R * T + Cc] = tile;
-    if (tile) atomicOr(reinterpret_cast<uint32_t *>(gh + tiles_bytes) + R * cwpr + (Cc >> 5), 1u << (Cc & 31));
+    if (tile) {
+        uint32_t *coarse = reinterpret_cast<uint32_t *>(gh + tiles_bytes);
+        atomicOr(coarse + R * cwpr + (Cc >> 5), 1u << (Cc & 31));
+        atomicOr(coarse + coarse_words + Cc * cwpr + (R >> 5), 1u << (R & 31));
+    }
 }
 
 // ------------------------------------------------------------------------- predicate / FK arrays
@@ -720,6 +725,7 @@ ag_status make_grid_dev(const ag_params *p, const ag_grid *g, int64_t env_id0, i
     d.T = (g->S + 7) / 8; d.cwpr = (d.T + 31) / 32;
     d.hier = d.T <= AG_HIER_MAX_T ? reinterpret_cast<const unsigned char *>(g->hier) : nullptr;   // larger maps: the row walk
     d.hier_tiles_bytes = (int32_t)((((int64_t)d.T * d.T + 1) & ~(int64_t)1) * 8);
+    d.hier_coarse_words = (int32_t)(((int64_t)d.T * d.cwpr + 3) & ~(int64_t)3);
     d.hier_bytes = (int32_t)ag_grid_hier_bytes(g->S);
     d.side = g->side; d.half = g->env_size / 2.0; d.inv_side = 1.0 / g->side;
     d.margin = 1e-9 * g->env_size;
@@ -894,7 +900,8 @@ ag_status ag_grid_pack_hier(const uint32_t *bits, int32_t S, int32_t n_grids, in
     cudaError_t e = cudaMemsetAsync(hier, 0, (size_t)hb * n_grids, (cudaStream_t)stream);
     if (e != cudaSuccess) return (ag_status)e;
     k_grid_pack_hier<<<blocks_for((int64_t)T * T * n_grids), AG_BLOCK, 0, (cudaStream_t)stream>>>(
-        bits, S, wpr, n_grids, grid_stride_words, reinterpret_cast<unsigned char *>(hier), T, cwpr, tb, hb);
+        bits, S, wpr, n_grids, grid_stride_words, reinterpret_cast<unsigned char *>(hier), T, cwpr, tb,
+        ((int64_t)T * cwpr + 3) & ~(int64_t)3, hb);
     return launched();
 }
 

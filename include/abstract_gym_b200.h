@@ -88,8 +88,9 @@ typedef struct ag_grid {
                                       * to an even count), tile (R, C) holding the 8x8 block of cells with bit (r%8)*8 + c%8 for
                                       * cell (8R + r%8, 8C + c%8); then a T x T summary bitmap, ceil(T/32) words per row (padded
                                       * to a multiple of 4 words), bit C%32 of word R*ceil(T/32) + C/32 set iff tile (R, C) has
-                                      * an occupied cell.  With it the FAST engine walks a link over the summary (8x fewer lines)
-                                      * and looks at the cells of occupied tiles only. */
+                                      * an occupied cell; then the same bitmap transposed (bit R%32 of word C*ceil(T/32) + R/32).
+                                      * With it the FAST engine walks a link over the summary along its minor axis (8x fewer,
+                                      * at most T/sqrt(2) lines) and looks at the cells of occupied tiles only. */
 } ag_grid;
 
 /* Collision engine selection. All three return identical flags (tests/test_gpu_parity.py):
