@@ -287,9 +287,11 @@ __device__ __forceinline__ int arm_fast_list(const FastList *fl, const ArmF &a, 
 __device__ __forceinline__ int round_magic(float v) { return __float_as_int(v + 12582912.0f) - 0x4B400000; }
 
 // The traversal walks the bit grid line by line: a "line" is a row of the row-major bits, or a column of the
-// transposed copy; positions within a line are columns resp. rows.  A link is walked along its MINOR axis
-// (a steep link by rows, a shallow one by columns, when the grid carries the transposed copy): at most
-// len/side/sqrt(2) lines instead of up to len/side, and on average 0.37 instead of 0.64 of it.
+// transposed copy; positions within a line are columns resp. rows.  When the grid carries the transposed copy the
+// lines run along the link's MAJOR axis (rows for a shallow link, columns for a steep one), so that the link crosses
+// as few lines as possible: at most len/side/sqrt(2) instead of up to len/side, on average 0.37 instead of 0.64 of it;
+// a line's position interval then spans |dp/dl| >= 1 cells.  (Until late in round 2 the choice was the other way
+// round -- most lines, one-cell intervals: 20 % slower on the 256 x 256 maps.)
 struct LinkScan {
     float p0x, p0y, p1x, p1y, side;
     LinkF L;
@@ -343,7 +345,8 @@ __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, co
     const float va = fmaf(-p0y, C.inv_side, roff), vb = fmaf(-p1y, C.inv_side, roff);    // rows of the end points
     LinkScan K;
     K.p0x = p0x; K.p0y = p0y; K.p1x = p1x; K.p1y = p1y; K.side = C.side; K.have_link = false; K.result = 0;
-    K.swapped = (V.bits_t != nullptr) && (fabsf(dx) > fabsf(dy));
+    // lines along the link's major axis: rows for a shallow link, columns (transposed copy) for a steep one
+    K.swapped = (V.bits_t != nullptr) && (fabsf(dy) > fabsf(dx));
     // line coordinate l (rows, or columns when swapped) and position coordinate p of the two end points
     const float la = K.swapped ? ua : va, lb = K.swapped ? ub : vb;
     const float pa = K.swapped ? va : ua, pb = K.swapped ? vb : ub;
@@ -352,7 +355,8 @@ __device__ __forceinline__ int link_fast(const GridDev &G, const GridView &V, co
     l_lo = max(l_lo, 0); l_hi = min(l_hi, S1);
     const float pseg_lo = fminf(pa, pb), pseg_hi = fmaxf(pa, pb);
     const uint32_t *linep = (K.swapped ? V.bits_t : V.bits) + l_lo * G.wpr;
-    // d(line coordinate) along the link vs d(position coordinate): |dl| >= |dp| when walking the minor axis
+    // d(line coordinate) along the link vs d(position coordinate): |dl| <= |dp| with the transposed copy; a link
+    // that is more than 64 positions per line (nearly parallel to the lines) is not tracked
     const float dl = lb - la, dp = pb - pa;
     const bool tracked = (l_hi - l_lo >= 2) && (fabsf(dl) * 64.0f >= fabsf(dp));
     if (!tracked) {

@@ -81,8 +81,11 @@ constexpr int LB = 256, LW = LB / 32;
 #ifndef AG_LUT_RING
 #define AG_LUT_RING 8
 #endif
-constexpr int RING = AG_LUT_RING;
-static_assert((RING & (RING - 1)) == 0 && RING >= 4, "ring slots: a power of two");
+#ifndef AG_CMAP_RING
+#define AG_CMAP_RING AG_LUT_RING
+#endif
+static_assert((AG_LUT_RING & (AG_LUT_RING - 1)) == 0 && AG_LUT_RING >= 4, "ring slots: a power of two");
+static_assert((AG_CMAP_RING & (AG_CMAP_RING - 1)) == 0 && AG_CMAP_RING >= 4, "ring slots: a power of two");
 
 constexpr double PHASE_MAGIC = 6755399441055744.0;       // 1.5 * 2^52: the add rounds to an integer in the low word
 constexpr double TWO_PI = 6.283185307179586476925;
@@ -523,6 +526,7 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
               const __grid_constant__ RolloutDev A, const __grid_constant__ LutConst L) {
     extern __shared__ __align__(16) unsigned char smem_grid[];  // the staged grid (layout of stage_grid), then SlowShared
     __shared__ __align__(16) float2 s_lut1[CMAP ? 1 : N1], s_lut2[CMAP ? 1 : N2];
+    constexpr int RING = CMAP ? AG_CMAP_RING : AG_LUT_RING;     // the table-arm form keeps its tables in static shared memory
     __shared__ __align__(16) float2 s_ring[LW][RING][32];   // action rows t .. t+RING-1 of each warp's tile (cp.async)
     __shared__ FastList s_fl;
     __shared__ float s_hz[2 * AG_LIST_MAX];
