@@ -883,7 +883,7 @@ bool rollout_lut_applies(const ag_params &P, const GridDev &G, const RolloutDev 
     return !legacy && G.stage && G.n_grids == 1 && G.S <= 32 && !P.choose_j_tar && (!rec || A.zfill) && budget;
 }
 
-// ---- the library-owned buffers of the configuration-space maps: a few entries per process, found by (device, grid
+// ---- the library-owned buffers of the configuration-space maps: up to 32 entries (33 KB each) per process, found by (device, grid
 // pointers, parameters); the CONTENT is validated on the device by every launch (k_cspace_build), so a grid that was
 // rewritten in place, or a new grid at a recycled address, just rebuilds the entry.
 namespace {
@@ -895,7 +895,7 @@ struct CmapEntry {
     uint32_t *buf = nullptr;
     unsigned long long last_use = 0;
 };
-constexpr int CMAP_ENTRIES = 8;
+constexpr int CMAP_ENTRIES = 32;
 std::mutex g_cmap_mutex;
 CmapEntry g_cmap[CMAP_ENTRIES];
 unsigned long long g_cmap_clock = 0;
