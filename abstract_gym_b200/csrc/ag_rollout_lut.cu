@@ -85,6 +85,9 @@ constexpr int LB = 256, LW = LB / 32;
 #define AG_CMAP_RING AG_LUT_RING
 #endif
 static_assert((AG_LUT_RING & (AG_LUT_RING - 1)) == 0 && AG_LUT_RING >= 4, "ring slots: a power of two");
+#ifndef AG_CMAP_LAZY_DRAW
+#define AG_CMAP_LAZY_DRAW 1
+#endif
 static_assert((AG_CMAP_RING & (AG_CMAP_RING - 1)) == 0 && AG_CMAP_RING >= 4, "ring slots: a power of two");
 
 constexpr double PHASE_MAGIC = 6755399441055744.0;       // 1.5 * 2^52: the add rounds to an integer in the low word
@@ -149,9 +152,18 @@ struct PoseDraw {
 };
 enum { PD_VALID = 1, PD_DREW = 2, PD_STUCK = 4 };
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// cmap_a: shared-window address of the configuration-space map, or 0.  A candidate whose bin is CLEAR is certainly
+// collision-free (the map's guarantee): accepted without any arithmetic on the arm.
 AG_COLD PoseDraw draw_valid_pose(const ag_params &P, const GridDev &G, const FastConst &C,
                                                  const unsigned char *smem_grid, const FastList *fl, uint32_t rc,
-                                                 const double *reset_u_env, int32_t R, uint64_t seed, uint64_t gid) {
+                                                 const double *reset_u_env, int32_t R, uint64_t seed, uint64_t gid,
+                                                 uint32_t cmap_a = 0u) {
     const GridView V = thread_view(G, const_cast<unsigned char *>(smem_grid), (int64_t)gid);
     PoseDraw o;
     o.j1 = 0.0; o.j2 = 0.0; o.info = PD_VALID;
@@ -169,6 +181,12 @@ AG_COLD PoseDraw draw_valid_pose(const ag_params &P, const GridDev &G, const Fas
         ++rc; ++tries;
         o.j1 = __dmul_rn(__dmul_rn(u0, 3.141592653589793), 2.0);    // scene_0.py:180  rand()*pi*2.0
         o.j2 = __dmul_rn(__dmul_rn(u1, 3.141592653589793), 2.0);    // :181
+        if (cmap_a != 0u && o.j1 < 1048576.0 && o.j2 < 1048576.0) {        // candidates are in [0, 2 pi) unless scripted
+            const uint32_t x1 = (uint32_t)__double2loint(fma(o.j1, 4294967296.0 / TWO_PI, PHASE_MAGIC));
+            const uint32_t x2 = (uint32_t)__double2loint(fma(o.j2, 4294967296.0 / TWO_PI, PHASE_MAGIC));
+            const uint32_t bit = ((x1 >> (32 - CB1)) << CB2) | (x2 >> (32 - CB2));
+            if (((lds_u32(cmap_a + ((bit >> 3) & ~3u)) >> (bit & 31u)) & 1u) == 0u) { colliding = false; continue; }
+        }
         const int d = fast_decide<BP_LIST>(P, G, V, fl, C, o.j1, o.j2, false);
         axis += d >> 2;
         colliding = (d & 1) != 0;
@@ -186,7 +204,7 @@ AG_COLD PoseDraw draw_valid_pose(const ag_params &P, const GridDev &G, const Fas
 template <bool RECORD>
 __device__ __forceinline__ void settle_step(const ag_params &P, const GridDev &G, const FastConst &C, const RolloutDev &A,
                                             SlowShared &ss, const FastList *fl, unsigned long long *s_acc,
-                                            const unsigned char *smem_grid, float thr_clean, int64_t e) {
+                                            const unsigned char *smem_grid, float thr_clean, int64_t e, uint32_t cmap_a) {
     const int x = threadIdx.x;
     const int t = ss.t[x] - 1;                                                   // the step being settled (ss.t: where the loop resumes)
     const int c = ss.cr[x] & 3, r = (ss.cr[x] >> 2) & 3;                         // the float32 verdicts: 0 / 1 certain, 2 undecided
@@ -231,7 +249,7 @@ __device__ __forceinline__ void settle_step(const ag_params &P, const GridDev &G
             } else {                                                             // second collision of this tile: draw now
                 const PoseDraw pd = draw_valid_pose(P, G, C, smem_grid, fl, ss.rc[x],
                                                     A.reset_u ? A.reset_u + e * A.R * 2 : nullptr, A.R, A.seed,
-                                                    (uint64_t)(A.env_id0 + e));
+                                                    (uint64_t)(A.env_id0 + e), cmap_a);
                 if (pd.info & PD_DREW) { q1 = pd.j1; q2 = pd.j2; }
                 ss.rc[x] = pd.rc;
                 info = pd.info;
@@ -513,12 +531,6 @@ __device__ __forceinline__ TableArm table_arm(double q1, double q2, double phase
     return a;
 }
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-
 // CMAP = true: the hot loop consults the configuration-space map instead of computing the table arm (scene-wide target only)
 template <bool HAS_ACT, bool RECORD, bool M3, bool CMAP>
 __global__ void __launch_bounds__(LB, AG_LUT_BLOCKS_PER_SM)
@@ -603,11 +615,17 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
                 }
             }
             if (RECORD && A.zfill) zero_fill_warp(A, tile * 32);
-            // the next valid reset pose, drawn by all lanes together
-            const PoseDraw pd = draw_valid_pose(P, G, C, smem_grid, &s_fl, rc0,
-                                                A.reset_u ? A.reset_u + ec * A.R * 2 : nullptr, A.R, A.seed,
-                                                (uint64_t)(A.env_id0 + ec));
-            ss.cq1[x] = pd.j1; ss.cq2[x] = pd.j2; ss.crc[x] = pd.rc; ss.cinfo[x] = pd.info;
+            if constexpr (CMAP && AG_CMAP_LAZY_DRAW) {
+                // Map form: no pose is drawn ahead.  6 % of the lanes collide during a tile; the lane that does draws
+                // then (settle_step), and 86 % of its candidates are accepted by one look at the map.
+                ss.cinfo[x] = 0;
+            } else {
+                // the next valid reset pose, drawn by all lanes together
+                const PoseDraw pd = draw_valid_pose(P, G, C, smem_grid, &s_fl, rc0,
+                                                    A.reset_u ? A.reset_u + ec * A.R * 2 : nullptr, A.R, A.seed,
+                                                    (uint64_t)(A.env_id0 + ec));
+                ss.cq1[x] = pd.j1; ss.cq2[x] = pd.j2; ss.crc[x] = pd.rc; ss.cinfo[x] = pd.info;
+            }
             __syncwarp();
         }
         for (;;) {   // ---- resume loop: one pass per entry into the hot loop (fresh tile, or after a level-2 call)
@@ -814,7 +832,9 @@ k_rollout_lut(const __grid_constant__ ag_params P, const __grid_constant__ GridD
         }
         // ================================================================ level 2 (out-of-line calls), then resume
         ss.q1[x] = q1; ss.q2[x] = q2; ss.thr[x] = thr; ss.t[x] = t + 1; ss.cr[x] = event ? (cr | 16) : 0;
-        if (event) settle_step<RECORD>(P, G, C, A, ss, &s_fl, s_acc, smem_grid, L.thr_c, s_tile[x >> 5] * 32 + (threadIdx.x & 31));
+        if (event)
+            settle_step<RECORD>(P, G, C, A, ss, &s_fl, s_acc, smem_grid, L.thr_c, s_tile[x >> 5] * 32 + (threadIdx.x & 31),
+                                CMAP ? smem_u32(smem_grid + L.cmap_off) : 0u);
         __syncwarp();
         }   // resume loop
     }
