@@ -25,7 +25,7 @@
 // loop, level 2 = settle_step).  Results are therefore identical to the general kernel's and the reference's;
 // tests/test_gpu_parity.py runs all forms.
 //
-// Structure: a persistent grid (256-thread blocks, 2 per SM); every warp draws 32-env tiles from a global counter.
+// Structure: a persistent grid (one 512-thread block per SM); every warp draws 32-env tiles from a global counter.
 // Per tile: state -> registers, the next valid reset pose is drawn up front by all 32 lanes together (draw_valid_pose;
 // consumed on collision), then K steps of
 //   action (cp.async ring, RING - 1 rows ahead) -> 2 DADD -> test -> record (2 F2F + 2 STG) -> vote.
@@ -49,7 +49,7 @@ namespace {
 #define AG_LUT_B2 9
 #endif
 #ifndef AG_LUT_BLOCKS_PER_SM
-#define AG_LUT_BLOCKS_PER_SM 2
+#define AG_LUT_BLOCKS_PER_SM 1
 #endif
 
 // configuration-space map (CMAP form of the kernel): 2^CB1 x 2^CB2 bins over (joint_1, joint_2) mod 2pi, one bit each
@@ -73,16 +73,23 @@ static_assert(sizeof(CmapHeader) <= CMAP_HDR_WORDS * 4, "header");
 constexpr int B1 = AG_LUT_B1, B2 = AG_LUT_B2;            // bins: 2^B1 for link 1 (also the resolution of its hazard bit), 2^B2 for link 2
 constexpr int N1 = 1 << B1, N2 = 1 << B2;
 static_assert(B1 >= 9 && B2 >= 9 && B1 <= 11 && B2 <= 11, "sub-bin phase must fit 23 bits; tables must fit static shared memory");
-constexpr int LB = 256, LW = LB / 32;
+// One 512-thread block per SM: the same 16 warps as two blocks of 256, but one copy of the map, of the obstacle list and
+// of the block's bookkeeping per SM (+3 %; 640 threads at 96 registers spill and lose 6 %).
+#ifndef AG_LUT_BLOCK
+#define AG_LUT_BLOCK 512
+#endif
+constexpr int LB = AG_LUT_BLOCK, LW = LB / 32;
 // Action prefetch ring: every lane streams its own actions global -> shared with cp.async (LDGSTS), RING - 1 steps
 // ahead of their use; slot (t mod RING) of the warp's ring holds row t.  (Register prefetch does not work here: ptxas
 // gives all in-flight LDGs of the loop ONE scoreboard slot, so a consumer waits for every outstanding load and the
 // effective distance is a single step: profiles/r2b.)
+// 8 rows for the map form; the table-arm form keeps 20 KB of tables in static shared memory next to the rings (static
+// shared memory is capped at 48 KB) and stays at 4.  [Moving the rings into the dynamic segment measured 5-9 % slower.]
 #ifndef AG_LUT_RING
-#define AG_LUT_RING 8
+#define AG_LUT_RING 4
 #endif
 #ifndef AG_CMAP_RING
-#define AG_CMAP_RING AG_LUT_RING
+#define AG_CMAP_RING 8
 #endif
 static_assert((AG_LUT_RING & (AG_LUT_RING - 1)) == 0 && AG_LUT_RING >= 4, "ring slots: a power of two");
 #ifndef AG_CMAP_LAZY_DRAW
