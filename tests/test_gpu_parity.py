@@ -1049,7 +1049,7 @@ assert np.array_equal(rec["flags"].cpu().numpy(), orec["flags"]) and np.array_eq
 assert np.array_equal(sc.stats.cpu().numpy(), ostats) and np.array_equal(sc.robot.joint_1.cpu().numpy(), st.j1)
 print("pooled ok", int(ostats[0]))
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, AG_DENSE_POOLED="1")
+    env = dict(os.environ, AG_DENSE_POOLED="1", AG_GRID_FORM="transposed")   # the pooled kernel walks bits + transposed bits
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and "pooled ok" in r.stdout, r.stdout[-2000:]
 
