@@ -61,7 +61,9 @@ def build_debug(force: bool = False, verbose: bool = False) -> str:
     """the -DAG_DEBUG_BOUNDS library (csrc/ag_device.cuh AG_CHECK_INDEX); tests/test_gpu_parity.py runs a subset on it"""
     if not force and os.path.exists(DEBUG_LIB) and not _stale(DEBUG_LIB):
         return DEBUG_LIB
-    return build(verbose=verbose, out=DEBUG_LIB, defines=["-DAG_DEBUG_BOUNDS"])
+    # -split-compile: the debug library's speed does not matter, its build time does (the release library is built
+    # without it: split compilation changes the generated code slightly, and the measured numbers are the normal build's)
+    return build(verbose=verbose, out=DEBUG_LIB, defines=["-DAG_DEBUG_BOUNDS", "-split-compile", "0"])
 
 
 def build(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
