@@ -1329,3 +1329,43 @@ def test_grid_forms_rollout_vs_oracle(ag, torch_, oracle, form, monkeypatch):
         g = ag.BatchedOccupancyGrid(torch_.as_tensor(np.stack(occs), device="cuda"), n // n_maps)
         dg = g.device_grid("cuda") if hasattr(g, "device_grid") else g._grid
         assert (dg.hier is not None) == (form == "hier") and (dg.bits_t is not None) == (form == "transposed")
+
+
+@pytest.mark.gpu
+def test_map_form_random_scenes_vs_oracle(ag, torch_, oracle):
+    """the headline kernel's configuration-space map on random scene_0-class scenes: random small maps (1..8 occupied
+    cells, 5..32 cells per side), random link lengths and targets -- every recorded flag, reward, joint, the
+    final state and the episode counters against the oracle.  AG_SOAK=<n> runs n scenes instead of 6."""
+    rng = np.random.default_rng(2024)
+    n_scenes = int(os.environ.get("AG_SOAK", "6"))
+    n, K = 4096, 24
+    for it in range(n_scenes):
+        S = int(rng.integers(5, 33))
+        occ = np.zeros((S, S), np.uint8)
+        m = int(rng.integers(1, 9))
+        occ[rng.integers(0, S, m), rng.integers(0, S, m)] = 1
+        l1, l2 = float(rng.uniform(0.15, 0.6)), float(rng.uniform(0.15, 0.6))
+        ang = rng.uniform(0, 2 * np.pi)
+        rad = rng.uniform(0.0, l1 + l2)
+        target = (float(rad * np.cos(ang)), float(rad * np.sin(ang)))
+        j1, j2 = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+        actions = ((rng.random((K, n, 2)) - 0.5) * 0.1).astype(np.float32)
+        reset_u = rng.random((n, 40, 2))
+        grid = ag.OccupancyGrid(size=9, random_obstacle=False)
+        grid.load_from_matrix(occ)
+        robot = ag.BatchedTwoJointRobot(torch_.as_tensor(j1, device="cuda"), torch_.as_tensor(j2, device="cuda"), link_1=l1, link_2=l2)
+        sc = ag.BatchedScene(robot, grid, target_c=ag.Point(*target), engine="fast", seed=5 + it)
+        p = oracle.default_params()
+        p.link_1, p.link_2, p.target_x, p.target_y = l1, l2, target[0], target[1]
+        dp = sc.params()
+        p.reach_eps = dp.reach_eps                       # whatever tolerance the scene actually uses
+        rec = sc.rollout(K, actions=torch_.as_tensor(actions, device="cuda"), reset_u=torch_.as_tensor(reset_u, device="cuda"))
+        torch_.cuda.synchronize()
+        st = oracle.RolloutState(j1, j2)
+        orec, ostats = oracle.rollout(st, K, [oracle.grid_squares(occ)[0]], seed=5 + it, actions_f32=actions, reset_u=reset_u, params=p)
+        what = "scene %d: S=%d m=%d links=(%.3f, %.3f) target=(%.3f, %.3f)" % (it, S, m, l1, l2, target[0], target[1])
+        assert np.array_equal(rec["flags"].cpu().numpy(), orec["flags"]), what
+        assert np.array_equal(rec["reward"].cpu().numpy(), orec["reward"]), what
+        assert np.array_equal(rec["j1"].cpu().numpy(), orec["j1"]) and np.array_equal(rec["j2"].cpu().numpy(), orec["j2"]), what
+        assert np.array_equal(sc.robot.joint_1.cpu().numpy(), st.j1) and np.array_equal(sc.robot.joint_2.cpu().numpy(), st.j2), what
+        assert np.array_equal(sc.stats.cpu().numpy(), ostats), what
